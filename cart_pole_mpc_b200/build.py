@@ -1,0 +1,60 @@
+"""Builds libcpmpc.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+The library is deliberately NOT a torch extension: the drop-in boundary is a plain C ABI (include/cpmpc.h) that the
+reference's C++ / nanobind side can link without Python.  nvcc cross-compiles without a GPU.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(PKG_DIR, "libcpmpc.so")
+SOURCES = ["cpmpc_capi.cu"]
+HEADERS = ["solver_kernel.cuh", "dynamics.cuh", os.path.join("..", "..", "include", "cpmpc.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC",
+]
+
+
+def _nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; libcpmpc.so cannot be built")
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    lib_m = os.path.getmtime(LIB_PATH)
+    for f in SOURCES + HEADERS:
+        if os.path.getmtime(os.path.join(CSRC, f)) > lib_m:
+            return True
+    return False
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile the library if it is missing or older than its sources; returns its path."""
+    if not force and not is_stale():
+        return LIB_PATH
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    env = dict(os.environ)
+    # the image's CXX points at a wrapper without OpenMP; nvcc only needs a plain host g++
+    env.pop("CXX", None)
+    env.pop("CC", None)
+    proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True, env=env)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+    if verbose:
+        print(proc.stderr)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build_library(force=True, verbose=True))

@@ -1,0 +1,595 @@
+// C ABI of libcpmpc.so (declared in include/cpmpc.h).  Host logic only: validation, device buffers, launch
+// configuration, host<->device staging.  All arithmetic of the hot path is in solver_kernel.cuh.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/cpmpc.h"
+#include "solver_kernel.cuh"
+
+using namespace cpmpc;
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
+
+int Fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    const cudaError_t err_ = (expr);                                                                \
+    if (err_ != cudaSuccess) {                                                                      \
+      return Fail(CPMPC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err_));            \
+    }                                                                                               \
+  } while (0)
+
+int Pow2Ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace
+
+struct cpmpc_solver {
+  cpmpc_params params;
+  long long B = 0;
+  int device = 0;
+  int lanes = 1;   // L: lanes per instance
+  int grid = 0;    // persistent grid (1 warp per block)
+  size_t smem_bytes = 0;
+  KernelCfg cfg;
+  cudaStream_t stream = nullptr;
+  // persistent device state
+  double* d_prev = nullptr;
+  unsigned char* d_has_prev = nullptr;
+  double* d_u_guess = nullptr;
+  double* d_lm = nullptr;
+  double* d_iter_log = nullptr;
+  bool log_enabled = false;
+  // staging for the host-buffer entry points
+  double* d_states = nullptr;
+  double* d_dyn = nullptr;
+  double* d_sp = nullptr;
+  double* d_weights = nullptr;
+  double* d_u = nullptr;
+  double* d_pred = nullptr;
+  cpmpc_stats* d_stats = nullptr;
+  long long* d_stats_sum = nullptr;
+  double* d_controls = nullptr;
+  long long controls_capacity = 0;
+};
+
+namespace {
+
+using KernelFn = void (*)(const KernelCfg, const KernelIO);
+
+KernelFn SelectKernel(int lanes) {
+  switch (lanes) {
+    case 1: return cpmpc_solve_kernel<1, 1>;
+    case 2: return cpmpc_solve_kernel<2, 1>;
+    case 4: return cpmpc_solve_kernel<4, 1>;
+    case 8: return cpmpc_solve_kernel<8, 1>;
+    case 16: return cpmpc_solve_kernel<16, 1>;
+    default: return cpmpc_solve_kernel<32, 1>;
+  }
+}
+
+// Shared-memory layout of one instance (doubles).
+void BuildLayout(KernelCfg& k) {
+  int off = 0;
+  auto take = [&off](int n) {
+    const int o = off;
+    off += n;
+    return o;
+  };
+  const int W = k.W, NS = k.NS, nseg = k.nseg;
+  k.off_xs = take(4 * NS);
+  k.off_u = take(W);
+  k.off_xc = take(4 * NS);
+  k.off_uc = take(W);
+  k.off_dxs = take(4 * NS);
+  k.off_du = take(W);
+  k.off_phi = take(16 * nseg);
+  k.off_e = take(4 * nseg);
+  k.off_gam = take(4 * W);
+  k.off_gdu = take(4 * nseg);
+  k.off_M = take(4 * W);
+  k.off_Y = take(5 * W);
+  k.off_tl = take(W);
+  k.off_tinv = take(W);
+  k.off_gram = take(20);
+  k.off_sig = take(4);
+  k.off_inv_d = take(4);
+  k.off_moff = take(4);
+  // odd stride (in doubles) so that the same field of neighbouring instances falls into different banks
+  k.stride = off | 1;
+  const int R = 4 * nseg;
+  k.lm_rows = R;
+  k.lm_stride = R * W + (R + 1) * W + R * (R + 1) + 3 * R;
+}
+
+int Launch(cpmpc_solver* h, KernelIO io, cudaStream_t stream) {
+  KernelFn fn = SelectKernel(h->lanes);
+  io.B = h->B;
+  io.u_guess = h->d_u_guess;
+  io.prev = h->d_prev;
+  io.has_prev = h->d_has_prev;
+  io.lm_scratch = h->d_lm;
+  io.iter_log = h->log_enabled ? h->d_iter_log : nullptr;
+  fn<<<h->grid, 32, h->smem_bytes, stream>>>(h->cfg, io);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return CPMPC_OK;
+}
+
+int EnsureStaging(cpmpc_solver* h) {
+  if (h->d_states != nullptr) return CPMPC_OK;
+  const long long B = h->B;
+  const int W = h->cfg.W;
+  CUDA_TRY(cudaMalloc(&h->d_states, sizeof(double) * B * 4));
+  CUDA_TRY(cudaMalloc(&h->d_dyn, sizeof(double) * B * 9));
+  CUDA_TRY(cudaMalloc(&h->d_sp, sizeof(double) * B));
+  CUDA_TRY(cudaMalloc(&h->d_weights, sizeof(double) * B * CPMPC_WEIGHTS_STRIDE));
+  CUDA_TRY(cudaMalloc(&h->d_u, sizeof(double) * B * W));
+  CUDA_TRY(cudaMalloc(&h->d_pred, sizeof(double) * B * W * 4));
+  CUDA_TRY(cudaMalloc(&h->d_stats, sizeof(cpmpc_stats) * B));
+  CUDA_TRY(cudaMalloc(&h->d_stats_sum, sizeof(long long) * 4));
+  return CPMPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* cpmpc_last_error(void) { return g_last_error.c_str(); }
+int cpmpc_version(void) { return CPMPC_VERSION; }
+int64_t cpmpc_launch_count(void) { return g_launches.load(); }
+
+void cpmpc_default_params(cpmpc_params* p) {
+  if (p == nullptr) return;
+  p->control_dt = 0.01;
+  p->window_length = 40;
+  p->state_spacing = 10;
+  p->max_iterations = 8;
+  p->relative_exit_tol = 1.0e-5;
+  p->absolute_first_derivative_tol = 1.0e-6;
+  p->equality_penalty_initial = 1.0;
+  p->u_guess_sinusoid_amplitude = 10.0;
+  p->u_cost_weight = 0.1;
+  p->u_derivative_cost_weight = 0.1;
+  p->b_x_final_cost_weight = 150.0;
+  p->th_final_cost_weight = -1.0;
+  p->b_x_dot_final_cost_weight = -1.0;
+  p->th_dot_final_cost_weight = -1.0;
+}
+
+int cpmpc_create(const cpmpc_params* params, int64_t batch, int device, cpmpc_handle* out) {
+  if (params == nullptr || out == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  // preconditions of Optimization::Optimization (optimization.cc:13-22) and CheckParams (nonlinear.cc:49-73)
+  if (!(params->control_dt > 0)) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "control_dt must be > 0");
+  if (params->window_length < 1) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "window_length must be >= 1");
+  if (params->state_spacing < 1 || params->window_length % params->state_spacing != 0) {
+    return Fail(CPMPC_ERR_INVALID_ARGUMENT, "state_spacing (" + std::to_string(params->state_spacing) +
+                                                ") must divide into window_length (" +
+                                                std::to_string(params->window_length) + ") cleanly");
+  }
+  if (params->max_iterations < 1) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "max_iterations must be >= 1");
+  if (!(params->u_cost_weight >= 0.0)) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "u_cost_weight must be >= 0");
+  if (!(params->u_derivative_cost_weight >= 0.0)) {
+    return Fail(CPMPC_ERR_INVALID_ARGUMENT, "u_derivative_cost_weight must be >= 0");
+  }
+  if (!(params->relative_exit_tol >= 0 && params->relative_exit_tol <= 1)) {
+    return Fail(CPMPC_ERR_INVALID_ARGUMENT, "relative_exit_tol must be in [0, 1]");
+  }
+  if (!(params->absolute_first_derivative_tol >= 0)) {
+    return Fail(CPMPC_ERR_INVALID_ARGUMENT, "absolute_first_derivative_tol must be >= 0");
+  }
+  if (!(params->equality_penalty_initial >= 0)) {
+    return Fail(CPMPC_ERR_INVALID_ARGUMENT, "equality_penalty_initial must be >= 0");
+  }
+  if (batch < 1) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "batch must be >= 1");
+  if (params->window_length > 4096) return Fail(CPMPC_ERR_UNSUPPORTED, "window_length > 4096 is not supported");
+
+  int n_dev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&n_dev));
+  if (device < 0 || device >= n_dev) return Fail(CPMPC_ERR_CUDA, "no such CUDA device: " + std::to_string(device));
+  CUDA_TRY(cudaSetDevice(device));
+
+  cpmpc_solver* h = new cpmpc_solver();
+  h->params = *params;
+  h->B = batch;
+  h->device = device;
+  KernelCfg& k = h->cfg;
+  std::memset(&k, 0, sizeof(k));
+  k.W = static_cast<int>(params->window_length);
+  k.S = static_cast<int>(params->state_spacing);
+  k.nseg = k.W / k.S;
+  k.NS = k.nseg + 1;
+  k.N = 4 * k.NS + k.W;
+  k.max_iter = static_cast<int>(params->max_iterations);
+  k.max_ls = 5;  // optimization.cc:76
+  k.dt = params->control_dt;
+  k.rel_tol = params->relative_exit_tol;
+  k.first_tol = params->absolute_first_derivative_tol;
+  k.abs_tol = 1.0e-12;      // nonlinear.hpp:75
+  k.pen_init = params->equality_penalty_initial;
+  k.pen_scale = 1.01;       // nonlinear.hpp:98
+  k.rho = 0.1;              // nonlinear.hpp:102
+  k.armijo_c1 = 1.0e-4;     // nonlinear.cc:121
+  k.lam_fail_init = 1.0e-2; // nonlinear.hpp:108
+  k.lam_dec_success = 0.1;  // nonlinear.hpp:111
+  k.lam_dec_restore = 0.8;  // nonlinear.hpp:114
+  k.lam_max = 1.0;          // nonlinear.hpp:117
+  k.lam_min = 0.0;          // nonlinear.hpp:120
+  k.w_u = params->u_cost_weight;
+  k.w_r = params->u_derivative_cost_weight;
+  k.wt[0] = params->b_x_final_cost_weight;
+  k.wt[1] = params->th_final_cost_weight;
+  k.wt[2] = params->b_x_dot_final_cost_weight;
+  k.wt[3] = params->th_dot_final_cost_weight;
+  k.x_clamp = 5.0;    // optimization.cc:320
+  k.u_clamp = 300.0;  // optimization.cc:327
+  BuildLayout(k);
+
+  // lanes per instance: one lane per shooting segment (power of two), overridable for experiments
+  int lanes = Pow2Ceil(k.nseg);
+  if (lanes > 32) lanes = 32;
+  if (const char* env = std::getenv("CPMPC_LANES")) {
+    const int v = std::atoi(env);
+    if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) lanes = v;
+  }
+  h->lanes = lanes;
+  const int groups_per_warp = 32 / lanes;
+  h->smem_bytes = sizeof(double) * static_cast<size_t>(k.stride) * groups_per_warp;
+
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (h->smem_bytes > static_cast<size_t>(prop.sharedMemPerBlockOptin)) {
+    delete h;
+    return Fail(CPMPC_ERR_UNSUPPORTED, "problem needs " + std::to_string(h->smem_bytes) +
+                                           " bytes of shared memory per warp, device offers " +
+                                           std::to_string(prop.sharedMemPerBlockOptin));
+  }
+  KernelFn fn = SelectKernel(lanes);
+  CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->smem_bytes)));
+  int blocks_per_sm = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, 32, h->smem_bytes));
+  if (blocks_per_sm < 1) {
+    delete h;
+    return Fail(CPMPC_ERR_UNSUPPORTED, "kernel does not fit on an SM");
+  }
+  const long long warps_needed = (batch + groups_per_warp - 1) / groups_per_warp;
+  const long long resident = static_cast<long long>(blocks_per_sm) * prop.multiProcessorCount;
+  h->grid = static_cast<int>(warps_needed < resident ? warps_needed : resident);
+
+  const long long n_groups = static_cast<long long>(h->grid) * groups_per_warp;
+  CUDA_TRY(cudaMalloc(&h->d_prev, sizeof(double) * batch * k.N));
+  CUDA_TRY(cudaMalloc(&h->d_has_prev, batch));
+  CUDA_TRY(cudaMemset(h->d_has_prev, 0, batch));
+  CUDA_TRY(cudaMemset(h->d_prev, 0, sizeof(double) * batch * k.N));
+  CUDA_TRY(cudaMalloc(&h->d_lm, sizeof(double) * n_groups * k.lm_stride));
+  CUDA_TRY(cudaMalloc(&h->d_u_guess, sizeof(double) * k.W));
+  // cold-start sinusoid with the host's libm, exactly as optimization.cc:63-67 evaluates it
+  std::vector<double> guess(k.W);
+  for (int i = 0; i < k.W; ++i) {
+    guess[i] = params->u_guess_sinusoid_amplitude *
+               std::sin(static_cast<double>(i) / static_cast<double>(k.W) * 2 * M_PI);
+  }
+  CUDA_TRY(cudaMemcpy(h->d_u_guess, guess.data(), sizeof(double) * k.W, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  *out = h;
+  return CPMPC_OK;
+}
+
+int cpmpc_destroy(cpmpc_handle h) {
+  if (h == nullptr) return CPMPC_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_prev);
+  cudaFree(h->d_has_prev);
+  cudaFree(h->d_u_guess);
+  cudaFree(h->d_lm);
+  cudaFree(h->d_iter_log);
+  cudaFree(h->d_states);
+  cudaFree(h->d_dyn);
+  cudaFree(h->d_sp);
+  cudaFree(h->d_weights);
+  cudaFree(h->d_u);
+  cudaFree(h->d_pred);
+  cudaFree(h->d_stats);
+  cudaFree(h->d_stats_sum);
+  cudaFree(h->d_controls);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return CPMPC_OK;
+}
+
+int64_t cpmpc_batch(cpmpc_handle h) { return h ? h->B : 0; }
+int64_t cpmpc_solution_dim(cpmpc_handle h) { return h ? h->cfg.N : 0; }
+
+int cpmpc_step_device(cpmpc_handle h, const double* states, const double* dyn_params, const double* set_points,
+                      const double* weights, double* u_out, double* pred_out, cpmpc_stats* stats_out,
+                      void* stream) {
+  if (h == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "null handle");
+  if (states == nullptr || dyn_params == nullptr || set_points == nullptr || u_out == nullptr) {
+    return Fail(CPMPC_ERR_INVALID_ARGUMENT, "states, dyn_params, set_points and u_out are required");
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  KernelIO io;
+  std::memset(&io, 0, sizeof(io));
+  io.states = states;
+  io.dyn = dyn_params;
+  io.set_points = set_points;
+  io.weights = weights;
+  io.u_out = u_out;
+  io.pred_out = pred_out;
+  io.stats = stats_out;
+  io.n_steps = 1;
+  io.sim = 0;
+  return Launch(h, io, static_cast<cudaStream_t>(stream));
+}
+
+int cpmpc_step(cpmpc_handle h, const double* states, const double* dyn_params, const double* set_points,
+               const double* weights, double* u_out, double* pred_out, cpmpc_stats* stats_out) {
+  if (h == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "null handle");
+  if (states == nullptr || dyn_params == nullptr || set_points == nullptr || u_out == nullptr) {
+    return Fail(CPMPC_ERR_INVALID_ARGUMENT, "states, dyn_params, set_points and u_out are required");
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (int rc = EnsureStaging(h)) return rc;
+  const long long B = h->B;
+  const int W = h->cfg.W;
+  cudaStream_t s = h->stream;
+  CUDA_TRY(cudaMemcpyAsync(h->d_states, states, sizeof(double) * B * 4, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->d_dyn, dyn_params, sizeof(double) * B * 9, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->d_sp, set_points, sizeof(double) * B, cudaMemcpyHostToDevice, s));
+  if (weights != nullptr) {
+    CUDA_TRY(cudaMemcpyAsync(h->d_weights, weights, sizeof(double) * B * CPMPC_WEIGHTS_STRIDE,
+                             cudaMemcpyHostToDevice, s));
+  }
+  if (int rc = cpmpc_step_device(h, h->d_states, h->d_dyn, h->d_sp, weights ? h->d_weights : nullptr, h->d_u,
+                                 pred_out ? h->d_pred : nullptr, stats_out ? h->d_stats : nullptr, s)) {
+    return rc;
+  }
+  CUDA_TRY(cudaMemcpyAsync(u_out, h->d_u, sizeof(double) * B * W, cudaMemcpyDeviceToHost, s));
+  if (pred_out != nullptr) {
+    CUDA_TRY(cudaMemcpyAsync(pred_out, h->d_pred, sizeof(double) * B * W * 4, cudaMemcpyDeviceToHost, s));
+  }
+  if (stats_out != nullptr) {
+    CUDA_TRY(cudaMemcpyAsync(stats_out, h->d_stats, sizeof(cpmpc_stats) * B, cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return CPMPC_OK;
+}
+
+int cpmpc_reset(cpmpc_handle h, const uint8_t* mask) {
+  if (h == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (mask == nullptr) {
+    CUDA_TRY(cudaMemset(h->d_has_prev, 0, h->B));
+    return CPMPC_OK;
+  }
+  std::vector<unsigned char> flags(h->B);
+  CUDA_TRY(cudaMemcpy(flags.data(), h->d_has_prev, h->B, cudaMemcpyDeviceToHost));
+  for (long long i = 0; i < h->B; ++i) {
+    if (mask[i]) flags[i] = 0;
+  }
+  CUDA_TRY(cudaMemcpy(h->d_has_prev, flags.data(), h->B, cudaMemcpyHostToDevice));
+  return CPMPC_OK;
+}
+
+int cpmpc_set_previous_solution(cpmpc_handle h, const double* solutions, const uint8_t* mask) {
+  if (h == nullptr || solutions == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  const int N = h->cfg.N;
+  if (mask == nullptr) {
+    CUDA_TRY(cudaMemcpy(h->d_prev, solutions, sizeof(double) * h->B * N, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(h->d_has_prev, 1, h->B));
+    return CPMPC_OK;
+  }
+  std::vector<unsigned char> flags(h->B);
+  CUDA_TRY(cudaMemcpy(flags.data(), h->d_has_prev, h->B, cudaMemcpyDeviceToHost));
+  for (long long i = 0; i < h->B; ++i) {
+    if (mask[i]) {
+      CUDA_TRY(cudaMemcpy(h->d_prev + i * N, solutions + i * N, sizeof(double) * N, cudaMemcpyHostToDevice));
+      flags[i] = 1;
+    }
+  }
+  CUDA_TRY(cudaMemcpy(h->d_has_prev, flags.data(), h->B, cudaMemcpyHostToDevice));
+  return CPMPC_OK;
+}
+
+int cpmpc_get_previous_solution(cpmpc_handle h, double* solutions_out, uint8_t* has_prev_out) {
+  if (h == nullptr || solutions_out == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaMemcpy(solutions_out, h->d_prev, sizeof(double) * h->B * h->cfg.N, cudaMemcpyDeviceToHost));
+  if (has_prev_out != nullptr) {
+    CUDA_TRY(cudaMemcpy(has_prev_out, h->d_has_prev, h->B, cudaMemcpyDeviceToHost));
+  }
+  return CPMPC_OK;
+}
+
+int cpmpc_enable_iteration_log(cpmpc_handle h, int enable) {
+  if (h == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (enable && h->d_iter_log == nullptr) {
+    const size_t bytes = sizeof(double) * h->B * h->cfg.max_iter * CPMPC_ITERLOG_STRIDE;
+    CUDA_TRY(cudaMalloc(&h->d_iter_log, bytes));
+    CUDA_TRY(cudaMemset(h->d_iter_log, 0, bytes));
+  }
+  h->log_enabled = enable != 0;
+  return CPMPC_OK;
+}
+
+int cpmpc_get_iteration_log(cpmpc_handle h, double* log_out) {
+  if (h == nullptr || log_out == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "null argument");
+  if (h->d_iter_log == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "iteration log was never enabled");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaMemcpy(log_out, h->d_iter_log, sizeof(double) * h->B * h->cfg.max_iter * CPMPC_ITERLOG_STRIDE,
+                      cudaMemcpyDeviceToHost));
+  return CPMPC_OK;
+}
+
+int cpmpc_sim_step_device(int64_t batch, double* states, const double* dyn_params, const double* u, double dt,
+                          const double* f_base, const double* f_mass, void* stream) {
+  if (batch < 1 || states == nullptr || dyn_params == nullptr || u == nullptr) {
+    return Fail(CPMPC_ERR_INVALID_ARGUMENT, "batch, states, dyn_params and u are required");
+  }
+  if (!(dt >= 0.0)) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "dt must be >= 0");  // simulator.cc:13
+  const int threads = 128;
+  const long long blocks = (batch + threads - 1) / threads;
+  cpmpc_sim_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      batch, states, dyn_params, u, dt, f_base, f_mass);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return CPMPC_OK;
+}
+
+int cpmpc_sim_step(int device, int64_t batch, double* states, const double* dyn_params, const double* u, double dt,
+                   const double* f_base, const double* f_mass) {
+  if (batch < 1 || states == nullptr || dyn_params == nullptr || u == nullptr) {
+    return Fail(CPMPC_ERR_INVALID_ARGUMENT, "batch, states, dyn_params and u are required");
+  }
+  for (int64_t i = 0; i < batch; ++i) {
+    if (!std::isfinite(u[i])) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "u must be finite");  // simulator.cc:14
+  }
+  CUDA_TRY(cudaSetDevice(device));
+  double *d_s = nullptr, *d_d = nullptr, *d_u = nullptr, *d_fb = nullptr, *d_fm = nullptr;
+  CUDA_TRY(cudaMalloc(&d_s, sizeof(double) * batch * 4));
+  CUDA_TRY(cudaMalloc(&d_d, sizeof(double) * batch * 9));
+  CUDA_TRY(cudaMalloc(&d_u, sizeof(double) * batch));
+  CUDA_TRY(cudaMemcpy(d_s, states, sizeof(double) * batch * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_d, dyn_params, sizeof(double) * batch * 9, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_u, u, sizeof(double) * batch, cudaMemcpyHostToDevice));
+  if (f_base != nullptr) {
+    CUDA_TRY(cudaMalloc(&d_fb, sizeof(double) * batch * 2));
+    CUDA_TRY(cudaMemcpy(d_fb, f_base, sizeof(double) * batch * 2, cudaMemcpyHostToDevice));
+  }
+  if (f_mass != nullptr) {
+    CUDA_TRY(cudaMalloc(&d_fm, sizeof(double) * batch * 2));
+    CUDA_TRY(cudaMemcpy(d_fm, f_mass, sizeof(double) * batch * 2, cudaMemcpyHostToDevice));
+  }
+  int rc = cpmpc_sim_step_device(batch, d_s, d_d, d_u, dt, d_fb, d_fm, nullptr);
+  if (rc == CPMPC_OK) {
+    const cudaError_t e = cudaMemcpy(states, d_s, sizeof(double) * batch * 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = Fail(CPMPC_ERR_CUDA, cudaGetErrorString(e));
+  }
+  cudaFree(d_s);
+  cudaFree(d_d);
+  cudaFree(d_u);
+  cudaFree(d_fb);
+  cudaFree(d_fm);
+  return rc;
+}
+
+int cpmpc_closed_loop_device(cpmpc_handle h, int64_t n_steps, double* states, const double* dyn_params,
+                             const double* set_points, const double* weights, double* controls_out,
+                             int64_t* stats_sum, void* stream) {
+  if (h == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "null handle");
+  if (n_steps < 1 || states == nullptr || dyn_params == nullptr || set_points == nullptr) {
+    return Fail(CPMPC_ERR_INVALID_ARGUMENT, "n_steps >= 1, states, dyn_params and set_points are required");
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  KernelIO io;
+  std::memset(&io, 0, sizeof(io));
+  io.states = states;
+  io.states_io = states;
+  io.dyn = dyn_params;
+  io.set_points = set_points;
+  io.weights = weights;
+  io.n_steps = n_steps;
+  io.sim = 1;
+  io.controls_out = controls_out;
+  io.stats_sum = reinterpret_cast<long long*>(stats_sum);
+  return Launch(h, io, static_cast<cudaStream_t>(stream));
+}
+
+int cpmpc_closed_loop(cpmpc_handle h, int64_t n_steps, double* states, const double* dyn_params,
+                      const double* set_points, const double* weights, double* controls_out,
+                      int64_t* stats_sum_out) {
+  if (h == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "null handle");
+  if (n_steps < 1 || states == nullptr || dyn_params == nullptr || set_points == nullptr) {
+    return Fail(CPMPC_ERR_INVALID_ARGUMENT, "n_steps >= 1, states, dyn_params and set_points are required");
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (int rc = EnsureStaging(h)) return rc;
+  const long long B = h->B;
+  cudaStream_t s = h->stream;
+  if (controls_out != nullptr && h->controls_capacity < B * n_steps) {
+    cudaFree(h->d_controls);
+    h->d_controls = nullptr;
+    CUDA_TRY(cudaMalloc(&h->d_controls, sizeof(double) * B * n_steps));
+    h->controls_capacity = B * n_steps;
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->d_states, states, sizeof(double) * B * 4, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->d_dyn, dyn_params, sizeof(double) * B * 9, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->d_sp, set_points, sizeof(double) * B, cudaMemcpyHostToDevice, s));
+  if (weights != nullptr) {
+    CUDA_TRY(cudaMemcpyAsync(h->d_weights, weights, sizeof(double) * B * CPMPC_WEIGHTS_STRIDE,
+                             cudaMemcpyHostToDevice, s));
+  }
+  CUDA_TRY(cudaMemsetAsync(h->d_stats_sum, 0, sizeof(long long) * 4, s));
+  if (int rc = cpmpc_closed_loop_device(h, n_steps, h->d_states, h->d_dyn, h->d_sp,
+                                        weights ? h->d_weights : nullptr, controls_out ? h->d_controls : nullptr,
+                                        reinterpret_cast<int64_t*>(h->d_stats_sum), s)) {
+    return rc;
+  }
+  CUDA_TRY(cudaMemcpyAsync(states, h->d_states, sizeof(double) * B * 4, cudaMemcpyDeviceToHost, s));
+  if (controls_out != nullptr) {
+    CUDA_TRY(cudaMemcpyAsync(controls_out, h->d_controls, sizeof(double) * B * n_steps, cudaMemcpyDeviceToHost, s));
+  }
+  if (stats_sum_out != nullptr) {
+    CUDA_TRY(cudaMemcpyAsync(stats_sum_out, h->d_stats_sum, sizeof(long long) * 4, cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return CPMPC_OK;
+}
+
+int cpmpc_measure_fp64_peak(int device, double* tflops_out) {
+  if (tflops_out == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "null argument");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  const int threads = 256;
+  const int blocks = prop.multiProcessorCount * 8;
+  const int iters = 4096;
+  double* d_out = nullptr;
+  CUDA_TRY(cudaMalloc(&d_out, sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  double best_ms = 1e30;
+  for (int rep = 0; rep < 5; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0));
+    cpmpc_dfma_probe_kernel<<<blocks, threads>>>(d_out, iters, 0.999999, 1e-7);
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best_ms) best_ms = ms;
+  }
+  g_launches.fetch_add(5);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  const double flops = 2.0 * 8.0 * 16.0 * static_cast<double>(iters) * threads * blocks;
+  *tflops_out = flops / (best_ms * 1e-3) / 1e12;
+  return CPMPC_OK;
+}
+
+}  // extern "C"

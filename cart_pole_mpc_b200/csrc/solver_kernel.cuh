@@ -1,0 +1,994 @@
+// Batched shooting-method MPC solve for sm_100a: one sub-warp "group" of L lanes per cart-pole instance.
+//
+// What one group does is what one call of pendulum::Optimization::Step does in the reference
+// (optimization/optimization.cc:39-97 -> mini_opt nonlinear.cc:75-158), re-organised around the structure of THIS
+// problem instead of a generic dense QP:
+//
+//   * lane s of a group owns shooting segment s: it rolls the dynamics out through S RK4 steps in registers
+//     (with the Jacobian chain in forward mode when linearising) — rows a1-a3 of SURVEY.md section 8a;
+//   * the equality-constrained QP (reference: dense column-pivoted QR + explicit Q + 37x37 Cholesky, qp.cc:679-729)
+//     is solved in condensed form.  With the shooting states eliminated forward through the linearised dynamics the
+//     Hessian over the W controls is  T + U^T D U : T is the tridiagonal control/control-rate Hessian (+ lambda),
+//     and U holds only the rows of the state sensitivities that carry a cost or a hard terminal constraint
+//     (4 rows when lambda = 0, 4*(NS-1) rows in Levenberg-Marquardt mode).  T is factored in O(W), the rows are
+//     handled through an (R x R) Schur complement.  The step dx is identical to the reference's null-space solution
+//     (the QP is strictly convex on the constraint null space, so the solution is unique);
+//   * the L1-merit polynomial line search, penalty update, LM state machine and exit tests follow
+//     nonlinear.cc:296-605 branch for branch, run in lock step by the groups of a warp.
+//
+// All per-instance state lives in shared memory (about 7 KB at W=40,S=10); HBM is touched only for the inputs,
+// the warm start and the results.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/cpmpc.h"
+#include "dynamics.cuh"
+
+namespace cpmpc {
+
+struct KernelCfg {
+  int W, S, NS, nseg, N, max_iter, max_ls;
+  int stride;  // doubles of shared memory per instance
+  int off_xs, off_u, off_xc, off_uc, off_dxs, off_du, off_phi, off_e, off_gam, off_gdu, off_M, off_Y, off_tl,
+      off_tinv, off_gram, off_sig, off_inv_d, off_moff;
+  int lm_rows;    // 4 * (NS - 1)
+  int lm_stride;  // doubles of global scratch per group for the Levenberg-Marquardt path
+  double dt, rel_tol, first_tol, abs_tol, pen_init, pen_scale, rho, armijo_c1;
+  double lam_fail_init, lam_dec_success, lam_dec_restore, lam_max, lam_min;
+  double w_u, w_r, wt[4];
+  double x_clamp, u_clamp;
+};
+
+struct KernelIO {
+  long long B;
+  const double* states;      // [B,4]
+  const double* dyn;         // [B,9]
+  const double* set_points;  // [B]
+  const double* weights;     // [B,6] or nullptr
+  const double* u_guess;     // [W] cold-start control guess (host libm, optimization.cc:63-67)
+  double* prev;              // [B,N] warm start, read then overwritten with the new solution
+  unsigned char* has_prev;   // [B]
+  double* u_out;             // [B,W]
+  double* pred_out;          // [B,W,4] or nullptr
+  cpmpc_stats* stats;        // [B] or nullptr
+  double* iter_log;          // [B,max_iter,27] or nullptr
+  double* lm_scratch;        // [n_groups, lm_stride]
+  // closed loop (n_sim_steps > 0): the plant state is integrated forward with u[0] after every solve
+  long long n_steps;         // number of Step()+Simulator::Step() rounds (1 and no plant update when sim == 0)
+  int sim;                   // 1 = closed loop
+  double* states_io;         // [B,4] in/out plant state when sim == 1
+  double* controls_out;      // [B,n_steps] or nullptr
+  long long* stats_sum;      // [4] or nullptr
+};
+
+// mini_opt enums (dependencies/mini_opt/include/mini_opt/structs.hpp:159-248), by declaration order.
+enum : int { SR_SUCCESS = 0, SR_MAX_ITERATIONS = 1, SR_FIRST_ORDER = 2, SR_POSITIVE_DERIVATIVE = 3,
+             SR_NON_FINITE = 4, SR_INVALID_ALPHA = 5 };
+enum : int { TS_MAX_ITERATIONS = 0, TS_ABS_TOL = 1, TS_REL_TOL = 2, TS_FIRST_ORDER = 3, TS_MAX_LAMBDA = 4,
+             TS_QP_INDEFINITE = 5, TS_REJECTED = -1 };
+enum : int { OS_NOMINAL = 0, OS_RESTORE_LM = 1 };
+
+template <int L>
+__device__ __forceinline__ double group_sum(double v, unsigned gmask) {
+#pragma unroll
+  for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+  return v;
+}
+
+__device__ __forceinline__ double clampd(double v, double lo, double hi) { return v < lo ? lo : (hi < v ? hi : v); }
+
+// Per-instance weights resolved from the batch defaults or the per-instance override.
+struct Weights {
+  double w_u, w_r;  // 0 when the corresponding cost family is absent (optimization.cc:270,296)
+  double wt[4];     // terminal weights; negative = hard equality (optimization.cc:236-267)
+};
+
+// Everything a group needs to address its instance.
+struct Ctx {
+  const KernelCfg* cfg;
+  double* sm;  // this instance's shared memory
+  double* lm;  // this group's global LM scratch
+  int gl;      // lane within the group
+  unsigned gmask;
+};
+
+#define CPMPC_GSYNC() __syncwarp(c.gmask)
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Cost terms over the controls (optimization.cc:270-301): 0.5 * sum of squared residuals for the columns owned by
+// this lane's segments.  `uu` is the control array in shared memory.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int L>
+__device__ __forceinline__ double control_cost_partial(const Ctx& c, const Weights& w, const double* uu,
+                                                       const double u_prev) {
+  const KernelCfg& k = *c.cfg;
+  double f = 0.0;
+  for (int s = c.gl; s < k.nseg; s += L) {
+    for (int i = 0; i < k.S; ++i) {
+      const int col = s * k.S + i;
+      const double uk = uu[col];
+      if (w.w_r > 0.0) {
+        if (col + 1 < k.W) {
+          const double r = (uk - uu[col + 1]) * w.w_r;
+          f += 0.5 * (r * r);
+        }
+        if (col == 0) {
+          const double r = (uk - u_prev) * w.w_r;
+          f += 0.5 * (r * r);
+        }
+      }
+      if (w.w_u > 0.0) {
+        const double r = uk * w.w_u;
+        f += 0.5 * (r * r);
+      }
+    }
+  }
+  return f;
+}
+
+// Terminal cost / terminal equality / initial-state equality residuals (optimization.cc:228-267), evaluated by
+// one lane from the shooting states `xx` in shared memory.
+__device__ __forceinline__ void boundary_terms(const KernelCfg& k, const Weights& w, const double* xx,
+                                               const double x_cur[4], const double set_point, double& f_term,
+                                               double& eq_bnd) {
+  constexpr double half_pi = 1.5707963267948966;
+  const double target[4] = {set_point, half_pi, 0.0, 0.0};
+  f_term = 0.0;
+  eq_bnd = 0.0;
+  // initial state rows (weight 1)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double d = xx[i] - x_cur[i];
+    if (i == 1) d = mod_pi(d);
+    eq_bnd += fabs(d);
+  }
+  const double* xN = xx + 4 * (k.NS - 1);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double d = xN[i] - target[i];
+    if (i == 1) d = mod_pi(d);
+    if (w.wt[i] >= 0.0) {
+      const double r = d * w.wt[i];
+      f_term += 0.5 * (r * r);
+    } else {
+      eq_bnd += fabs(d);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// One merit evaluation == EvaluateNonlinearErrors (nonlinear.cc:279-293) on the shooting states `xx` / controls `uu`.
+// Each lane integrates its own segments without Jacobians; the defects against the next shooting state are L1-summed.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int L>
+__device__ __forceinline__ void evaluate_errors(const Ctx& c, const DynConst& P, const Weights& w, const double* xx,
+                                                const double* uu, const double x_cur[4], const double set_point,
+                                                const double u_prev, double& f_out, double& eq_out) {
+  const KernelCfg& k = *c.cfg;
+  double eq = 0.0;
+  for (int s = c.gl; s < k.nseg; s += L) {
+    double x[4] = {xx[4 * s], xx[4 * s + 1], xx[4 * s + 2], xx[4 * s + 3]};
+    for (int i = 0; i < k.S; ++i) rk4_step<false>(P, x, uu[s * k.S + i], k.dt);
+    x[1] = mod_pi(x[1]);
+    const double* xn = xx + 4 * (s + 1);
+    eq += fabs(x[0] - xn[0]);
+    eq += fabs(mod_pi(x[1] - xn[1]));
+    eq += fabs(x[2] - xn[2]);
+    eq += fabs(x[3] - xn[3]);
+  }
+  double f = control_cost_partial<L>(c, w, uu, u_prev);
+  if (c.gl == 0) {
+    double ft, eb;
+    boundary_terms(k, w, xx, x_cur, set_point, ft, eb);
+    f += ft;
+    eq += eb;
+  }
+  f_out = group_sum<L>(f, c.gmask);
+  eq_out = group_sum<L>(eq, c.gmask);
+}
+
+// Tridiagonal LDL^T of T = diag(a_k) + offdiag(-w_r^2): a_k = w_u^2 + lambda + w_r^2 * n_k where n_k counts the
+// control-rate residuals touching u_k (2, or 1 for the last knot).  One lane; returns false on a non-positive pivot.
+__device__ __forceinline__ bool factor_tridiagonal(const KernelCfg& k, const Weights& w, const double lambda,
+                                                   double* tl, double* tinv) {
+  const double wu2 = w.w_u * w.w_u, wr2 = w.w_r * w.w_r;
+  const double off = -wr2;
+  double d_prev = 0.0;
+  bool ok = true;
+  for (int j = 0; j < k.W; ++j) {
+    const double a = wu2 + lambda + wr2 * ((j + 1 < k.W) ? 2.0 : 1.0);
+    double l = 0.0, d = a;
+    if (j > 0) {
+      l = off * tinv[j - 1];
+      d = a - l * off;
+    }
+    ok = ok && (d > 0.0);
+    tl[j] = l;
+    tinv[j] = 1.0 / d;
+    d_prev = d;
+  }
+  (void)d_prev;
+  return ok;
+}
+
+// In-place solve T y = r with the factorisation above (r has stride 1, length W).
+__device__ __forceinline__ void solve_tridiagonal(const int W, const double* tl, const double* tinv, double* r) {
+  for (int j = 1; j < W; ++j) r[j] -= tl[j] * r[j - 1];
+  r[W - 1] *= tinv[W - 1];
+  for (int j = W - 2; j >= 0; --j) r[j] = r[j] * tinv[j] - tl[j + 1] * r[j + 1];
+}
+
+struct SolveResult {
+  int termination;
+  int n_iter;
+  int n_ls;
+  int n_failed;
+  int last_step_result;
+  int opt_state;
+  double f, eq, penalty, lambda;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The whole Optimization::Step for one instance, executed by the L lanes of a group.  `active` is group-uniform;
+// inactive groups only take part in the warp-wide votes that keep the groups of a warp in lock step.
+// On entry the shooting state x(0) and the control guess are in shared memory (xs[0..3], u[]); on exit xs/u hold the
+// solution.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int L>
+__device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, const DynConst& P, const Weights& w,
+                                            const double x_cur[4], const double set_point, const double u_prev,
+                                            double* iter_log, SolveResult& res) {
+  const KernelCfg& k = *c.cfg;
+  double* xs = c.sm + k.off_xs;
+  double* u = c.sm + k.off_u;
+  double* xc = c.sm + k.off_xc;
+  double* uc = c.sm + k.off_uc;
+  double* dxs = c.sm + k.off_dxs;
+  double* du = c.sm + k.off_du;
+  double* Phi = c.sm + k.off_phi;
+  double* ev = c.sm + k.off_e;
+  double* Gam = c.sm + k.off_gam;
+  double* gdu = c.sm + k.off_gdu;
+  double* tl = c.sm + k.off_tl;
+  double* tinv = c.sm + k.off_tinv;
+  constexpr double half_pi = 1.5707963267948966;
+  const double target[4] = {set_point, half_pi, 0.0, 0.0};
+  const int W = k.W, S = k.S, NS = k.NS, nseg = k.nseg;
+
+  bool active = active_in;
+  double lambda = 0.0;  // params.lambda_initial (nonlinear.hpp:104)
+  double penalty = k.pen_init;
+  int opt_state = OS_NOMINAL;
+  double cur_f = 0.0, cur_eq = 0.0;  // Errors at the current variables
+  bool have_cur = false;
+  bool tri_valid = false;  // factorisation of T for lambda == 0 is cached across iterations
+  res.termination = TS_MAX_ITERATIONS;
+  res.n_iter = 0;
+  res.n_ls = 0;
+  res.n_failed = 0;
+  res.last_step_result = SR_SUCCESS;
+
+  for (int iter = 0; iter < k.max_iter; ++iter) {
+    if (!__any_sync(0xffffffffu, active)) break;
+
+    double f0 = 0.0, eq0 = 0.0, d_f = 0.0, d_eq = 0.0;
+    bool qp_ok = true;
+    const double lambda_in = lambda;
+
+    if (active) {
+      // ---- linearise: RK4 with the Jacobian chain, forward-mode accumulation inside the segment -----------------
+      double eq_part = 0.0;
+      for (int s = c.gl; s < nseg; s += L) {
+        double x[4] = {xs[4 * s], xs[4 * s + 1], xs[4 * s + 2], xs[4 * s + 3]};
+        double* Ph = Phi + 16 * s;
+        for (int i = 0; i < S; ++i) {
+          double A[16], Bv[4];
+          const int col = s * S + i;
+          rk4_step_jac(P, x, u[col], k.dt, A, Bv);
+          if (i == 0) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) Ph[q] = A[q];
+          } else {
+            // Phi <- A Phi
+            double T[16];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                T[4 * r + j] = A[4 * r] * Ph[j] + A[4 * r + 1] * Ph[4 + j] + A[4 * r + 2] * Ph[8 + j] +
+                               A[4 * r + 3] * Ph[12 + j];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) Ph[q] = T[q];
+            // Gamma_j <- A Gamma_j for the earlier knots of this segment
+            for (int j = s * S; j < col; ++j) {
+              const double g0 = Gam[j], g1 = Gam[W + j], g2 = Gam[2 * W + j], g3 = Gam[3 * W + j];
+#pragma unroll
+              for (int r = 0; r < 4; ++r)
+                Gam[r * W + j] = A[4 * r] * g0 + A[4 * r + 1] * g1 + A[4 * r + 2] * g2 + A[4 * r + 3] * g3;
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 4; ++r) Gam[r * W + col] = Bv[r];
+        }
+        x[1] = mod_pi(x[1]);
+        const double* xn = xs + 4 * (s + 1);
+        const double e0 = x[0] - xn[0], e1 = mod_pi(x[1] - xn[1]), e2 = x[2] - xn[2], e3 = x[3] - xn[3];
+        ev[4 * s] = e0;
+        ev[4 * s + 1] = e1;
+        ev[4 * s + 2] = e2;
+        ev[4 * s + 3] = e3;
+        eq_part += fabs(e0) + fabs(e1) + fabs(e2) + fabs(e3);
+      }
+      double f_part = control_cost_partial<L>(c, w, u, u_prev);
+      if (c.gl == 0) {
+        double ft, eb;
+        boundary_terms(k, w, xs, x_cur, set_point, ft, eb);
+        f_part += ft;
+        eq_part += eb;
+      }
+      f0 = group_sum<L>(f_part, c.gmask);
+      eq0 = group_sum<L>(eq_part, c.gmask);
+      if (have_cur) {
+        // Same variables as the accepted line-search candidate: the reference gets bit-identical numbers from both
+        // code paths; keep the line-search values so the merit comparison is self-consistent.
+        f0 = cur_f;
+        eq0 = cur_eq;
+      } else {
+        cur_f = f0;
+        cur_eq = eq0;
+        have_cur = true;
+      }
+      CPMPC_GSYNC();
+
+      if (!isfinite(f0) || !isfinite(eq0)) {
+        // The reference throws here (nonlinear.cc:356-357); the batch reports it per instance instead.
+        res.termination = TS_REJECTED;
+        active = false;
+      }
+    }
+
+    if (active) {
+      // ---- QP in condensed form --------------------------------------------------------------------------------
+      const bool lm = lambda > 0.0;
+      const int R = lm ? k.lm_rows : 4;
+      double* U = lm ? c.lm : (c.sm + k.off_M);                          // [R][W]
+      double* Y = lm ? (c.lm + (size_t)R * W) : (c.sm + k.off_Y);         // [R+1][W]  (last row: T^-1 g)
+      double* Gm = lm ? (c.lm + (size_t)(2 * R + 1) * W) : (c.sm + k.off_gram);  // [R][R+1] (last col: U y_g)
+      double* sig = lm ? (Gm + (size_t)R * (R + 1)) : (c.sm + k.off_sig);        // [R]
+      double* inv_d = lm ? (sig + R) : (c.sm + k.off_inv_d);                     // [R]
+      double* moff = lm ? (inv_d + R) : (c.sm + k.off_moff);                     // [R] rhs offsets
+      const int node0 = lm ? 1 : (NS - 1);  // node of row 0
+
+      // (1) factor T (one lane) and the state offsets m_s (dx at the nodes for du = 0)
+      if (c.gl == 0) {
+        if (lm || !tri_valid) qp_ok = factor_tridiagonal(k, w, lambda, tl, tinv);
+        double m[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          double d = xs[i] - x_cur[i];
+          if (i == 1) d = mod_pi(d);
+          m[i] = -d;
+        }
+        dxs[0] = m[0];
+        dxs[1] = m[1];
+        dxs[2] = m[2];
+        dxs[3] = m[3];
+        for (int s = 0; s < nseg; ++s) {
+          const double* Ph = Phi + 16 * s;
+          double n[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+            n[r] = Ph[4 * r] * m[0] + Ph[4 * r + 1] * m[1] + Ph[4 * r + 2] * m[2] + Ph[4 * r + 3] * m[3] + ev[4 * s + r];
+          const int node = s + 1;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) m[r] = n[r];
+          if (node >= node0) {
+            const int row = 4 * (node - node0);
+            const bool terminal = node == NS - 1;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              double invd, off;
+              if (terminal) {
+                double d = xs[4 * node + i] - target[i];
+                if (i == 1) d = mod_pi(d);
+                if (w.wt[i] < 0.0) {
+                  invd = 0.0;  // hard row
+                  off = m[i] + d;
+                } else {
+                  const double dd = w.wt[i] * w.wt[i] + lambda;
+                  if (dd > 0.0) {
+                    invd = 1.0 / dd;
+                    off = m[i] + (w.wt[i] * w.wt[i] * d) * invd;
+                  } else {
+                    invd = -1.0;  // inactive row
+                    off = 0.0;
+                  }
+                }
+              } else {
+                invd = 1.0 / lambda;
+                off = m[i];
+              }
+              inv_d[row + i] = invd;
+              moff[row + i] = off;
+            }
+          }
+        }
+      }
+      tri_valid = !lm;
+
+      // (2) rows of U: sensitivities of the node states to the controls, propagated through later segments
+      for (int s = c.gl; s < nseg; s += L) {
+        for (int i = 0; i < S; ++i) {
+          const int col = s * S + i;
+          double v[4] = {Gam[col], Gam[W + col], Gam[2 * W + col], Gam[3 * W + col]};
+          if (lm) {
+            for (int node = 1; node <= s; ++node)
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                U[(size_t)(4 * (node - 1) + r) * W + col] = 0.0;
+                Y[(size_t)(4 * (node - 1) + r) * W + col] = 0.0;
+              }
+          }
+          for (int node = s + 1; node <= NS - 1; ++node) {
+            if (node > s + 1) {
+              const double* Ph = Phi + 16 * (node - 1);
+              double n[4];
+#pragma unroll
+              for (int r = 0; r < 4; ++r)
+                n[r] = Ph[4 * r] * v[0] + Ph[4 * r + 1] * v[1] + Ph[4 * r + 2] * v[2] + Ph[4 * r + 3] * v[3];
+#pragma unroll
+              for (int r = 0; r < 4; ++r) v[r] = n[r];
+            }
+            if (node >= node0) {
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                U[(size_t)(4 * (node - node0) + r) * W + col] = v[r];
+                Y[(size_t)(4 * (node - node0) + r) * W + col] = v[r];
+              }
+            }
+          }
+          // gradient of the control costs, c_u = J^T r (optimization.cc:270-301)
+          double g = 0.0;
+          const double uk = u[col];
+          if (w.w_r > 0.0) {
+            const double wr2 = w.w_r * w.w_r;
+            if (col + 1 < W) g += wr2 * (uk - u[col + 1]);
+            if (col > 0) g -= wr2 * (u[col - 1] - uk);
+            if (col == 0) g += wr2 * (uk - u_prev);
+          }
+          if (w.w_u > 0.0) g += (w.w_u * w.w_u) * uk;
+          Y[(size_t)R * W + col] = g;
+          du[col] = g;  // keep c_u for the directional derivative
+        }
+      }
+      CPMPC_GSYNC();
+      qp_ok = __shfl_sync(c.gmask, qp_ok ? 1 : 0, (c.gmask == 0xffffffffu) ? 0 : (__ffs(c.gmask) - 1)) != 0;
+
+      // (3) Y_r = T^-1 U_r^T and y_g = T^-1 g
+      for (int r = c.gl; r <= R; r += L) solve_tridiagonal(W, tl, tinv, Y + (size_t)r * W);
+      CPMPC_GSYNC();
+
+      // (4) Schur complement  Gm[i][j] = U_i . Y_j  (j == R: U_i . y_g)
+      for (int j = c.gl; j <= R; j += L) {
+        const double* yj = Y + (size_t)j * W;
+        for (int i = 0; i < R; ++i) {
+          const double* ui = U + (size_t)i * W;
+          double acc = 0.0;
+          for (int q = 0; q < W; ++q) acc += ui[q] * yj[q];
+          Gm[(size_t)i * (R + 1) + j] = acc;
+        }
+      }
+      CPMPC_GSYNC();
+
+      // (5) Cholesky of (Gm + diag(1/d)) and solve for the row multipliers (one lane)
+      if (c.gl == 0 && qp_ok) {
+        const int ld = R + 1;
+        for (int i = 0; i < R; ++i) {
+          if (inv_d[i] < 0.0) {
+            for (int j = 0; j < R; ++j) {
+              Gm[(size_t)i * ld + j] = 0.0;
+              Gm[(size_t)j * ld + i] = 0.0;
+            }
+            Gm[(size_t)i * ld + i] = 1.0;
+            sig[i] = 0.0;
+          } else {
+            Gm[(size_t)i * ld + i] += inv_d[i];
+            sig[i] = moff[i] - Gm[(size_t)i * ld + R];
+          }
+        }
+        for (int j = 0; j < R && qp_ok; ++j) {
+          double d = Gm[(size_t)j * ld + j];
+          for (int q = 0; q < j; ++q) d -= Gm[(size_t)j * ld + q] * Gm[(size_t)j * ld + q];
+          if (!(d > 0.0)) {
+            qp_ok = false;
+            break;
+          }
+          d = sqrt(d);
+          Gm[(size_t)j * ld + j] = d;
+          const double inv = 1.0 / d;
+          for (int i = j + 1; i < R; ++i) {
+            double sacc = Gm[(size_t)i * ld + j];
+            for (int q = 0; q < j; ++q) sacc -= Gm[(size_t)i * ld + q] * Gm[(size_t)j * ld + q];
+            Gm[(size_t)i * ld + j] = sacc * inv;
+          }
+        }
+        if (qp_ok) {
+          for (int i = 0; i < R; ++i) {
+            double sacc = sig[i];
+            for (int q = 0; q < i; ++q) sacc -= Gm[(size_t)i * ld + q] * sig[q];
+            sig[i] = sacc / Gm[(size_t)i * ld + i];
+          }
+          for (int i = R - 1; i >= 0; --i) {
+            double sacc = sig[i];
+            for (int q = i + 1; q < R; ++q) sacc -= Gm[(size_t)q * ld + i] * sig[q];
+            sig[i] = sacc / Gm[(size_t)i * ld + i];
+          }
+        }
+      }
+      CPMPC_GSYNC();
+      qp_ok = __shfl_sync(c.gmask, qp_ok ? 1 : 0, (c.gmask == 0xffffffffu) ? 0 : (__ffs(c.gmask) - 1)) != 0;
+
+      if (!qp_ok) {
+        // QP_INDEFINITE: Solve() returns before this iteration is logged (nonlinear.cc:103-105)
+        res.termination = TS_QP_INDEFINITE;
+        active = false;
+      } else {
+        // (6) du = -y_g - sum_r sig_r Y_r ; partial sums of c.dx and dx^T G dx over this lane's columns
+        double cdx = 0.0;
+        for (int s = c.gl; s < nseg; s += L) {
+          double acc[4] = {0.0, 0.0, 0.0, 0.0};
+          for (int i = 0; i < S; ++i) {
+            const int col = s * S + i;
+            double v = -Y[(size_t)R * W + col];
+            for (int r = 0; r < R; ++r) v -= sig[r] * Y[(size_t)r * W + col];
+            cdx += du[col] * v;  // du[] still holds c_u
+            du[col] = v;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] += Gam[r * W + col] * v;
+          }
+#pragma unroll
+          for (int r = 0; r < 4; ++r) gdu[4 * s + r] = acc[r];
+        }
+        CPMPC_GSYNC();
+
+        // (7) state steps by forward propagation; quadratic form; directional derivatives (nonlinear.cc:457-502)
+        double quad = 0.0;
+        const double wu2 = w.w_u * w.w_u, wr2 = w.w_r * w.w_r;
+        for (int s = c.gl; s < nseg; s += L) {
+          for (int i = 0; i < S; ++i) {
+            const int col = s * S + i;
+            const double a = wu2 + lambda + wr2 * ((col + 1 < W) ? 2.0 : 1.0);
+            const double v = du[col];
+            quad += a * v * v;
+            if (col + 1 < W) quad -= 2.0 * wr2 * v * du[col + 1];
+          }
+        }
+        if (c.gl == 0) {
+          double m[4] = {dxs[0], dxs[1], dxs[2], dxs[3]};
+          quad += lambda * (m[0] * m[0] + m[1] * m[1] + m[2] * m[2] + m[3] * m[3]);
+          for (int s = 0; s < nseg; ++s) {
+            const double* Ph = Phi + 16 * s;
+            double n[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+              n[r] = Ph[4 * r] * m[0] + Ph[4 * r + 1] * m[1] + Ph[4 * r + 2] * m[2] + Ph[4 * r + 3] * m[3] +
+                     gdu[4 * s + r] + ev[4 * s + r];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              m[r] = n[r];
+              dxs[4 * (s + 1) + r] = n[r];
+            }
+            quad += lambda * (m[0] * m[0] + m[1] * m[1] + m[2] * m[2] + m[3] * m[3]);
+          }
+          // terminal rows: cost gradient / Hessian, and the equality rows' A_i.dx
+          double deq_term = 0.0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            double d = xs[4 * (NS - 1) + i] - target[i];
+            if (i == 1) d = mod_pi(d);
+            if (w.wt[i] >= 0.0) {
+              const double w2 = w.wt[i] * w.wt[i];
+              cdx += (w2 * d) * m[i];
+              quad += w2 * m[i] * m[i];
+            } else {
+              deq_term += ((d > 0.0) ? 1.0 : ((d < 0.0) ? -1.0 : 0.0)) * m[i];
+            }
+          }
+          // every other equality row satisfies A_i.dx = -b_i by construction of dx
+          double l1_other = 0.0;
+          for (int q = 0; q < 4 * nseg; ++q) l1_other += fabs(ev[q]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) l1_other += fabs(dxs[i]);
+          d_eq = deq_term - l1_other;
+        }
+        CPMPC_GSYNC();
+        d_f = group_sum<L>(cdx, c.gmask);
+        quad = group_sum<L>(quad, c.gmask);
+        d_eq = group_sum<L>(d_eq, c.gmask);
+
+        // penalty update, inequality (18.36) (nonlinear.cc:112-118,484-502)
+        const double l1_eq = fmax(eq0, 2.220446049250313e-16);
+        const double new_penalty = (d_f + 0.5 * fmax(0.0, quad)) / ((1.0 - k.rho) * l1_eq);
+        if (new_penalty > penalty) penalty = new_penalty * k.pen_scale;
+      }
+    }
+
+    // ---- line search (nonlinear.cc:351-443), groups of the warp in lock step ---------------------------------------
+    const double phi0 = f0 + penalty * eq0;
+    const double dphi0 = d_f + penalty * d_eq;
+    const double linf = fmax(fabs(d_f), fabs(d_eq));
+    int step_result = SR_MAX_ITERATIONS;
+    bool ls_done = !active;
+    double alpha = 1.0;
+    double a_prev = 0.0, phi_prev = 0.0, a_prev2 = 0.0, phi_prev2 = 0.0;
+    double step_f = 0.0, step_eq = 0.0;
+    int n_steps = 0;
+    double* lrow = (iter_log != nullptr && active) ? iter_log + (size_t)iter * CPMPC_ITERLOG_STRIDE : nullptr;
+    for (int ls = 0; ls <= k.max_ls; ++ls) {
+      if (__all_sync(0xffffffffu, ls_done)) break;
+      if (!ls_done && ls > 0) {
+        // polynomial step-length selection (nonlinear.cc:418-443,531-605)
+        double new_alpha = 0.0;
+        bool valid;
+        if (ls == 1) {
+          const double numerator = phi_prev - dphi0 * a_prev - phi0;
+          valid = !(dphi0 > 0.0 || numerator <= 0.0);
+          new_alpha = -dphi0 * a_prev * a_prev / (2.0 * numerator);
+        } else {
+          const double a0 = a_prev2, a1 = a_prev;
+          const double m00 = a0 * a0 * a0, m01 = a0 * a0, m10 = a1 * a1 * a1, m11 = a1 * a1;
+          const double r0 = phi_prev2 - phi0 - dphi0 * a0;
+          const double r1 = phi_prev - phi0 - dphi0 * a1;
+          const double inv_det = 1.0 / (m00 * m11 - m10 * m01);
+          const double ca = (m11 * inv_det) * r0 + (-m01 * inv_det) * r1;
+          const double cb = (-m10 * inv_det) * r0 + (m00 * inv_det) * r1;
+          const double arg_sqrt = cb * cb - 3.0 * ca * dphi0;
+          valid = !(ca == 0.0 || arg_sqrt < -1.0e-12);
+          new_alpha = (-cb + sqrt(fmax(arg_sqrt, 0.0))) / (3.0 * ca);
+        }
+        if (!valid || !isfinite(new_alpha) || new_alpha <= 0.0 || new_alpha >= alpha) {
+          step_result = SR_INVALID_ALPHA;
+          ls_done = true;
+        } else {
+          alpha = new_alpha;
+        }
+      }
+      if (!ls_done) {
+        // retraction (optimization.cc:309-329): x + dx*alpha, wrap angles, clamp b_x and u
+        for (int q = c.gl; q < NS; q += L) {
+          const double b = __dadd_rn(xs[4 * q], __dmul_rn(dxs[4 * q], alpha));
+          const double t = __dadd_rn(xs[4 * q + 1], __dmul_rn(dxs[4 * q + 1], alpha));
+          xc[4 * q] = clampd(b, -k.x_clamp, k.x_clamp);
+          xc[4 * q + 1] = mod_pi(t);
+          xc[4 * q + 2] = __dadd_rn(xs[4 * q + 2], __dmul_rn(dxs[4 * q + 2], alpha));
+          xc[4 * q + 3] = __dadd_rn(xs[4 * q + 3], __dmul_rn(dxs[4 * q + 3], alpha));
+        }
+        for (int s = c.gl; s < nseg; s += L)
+          for (int i = 0; i < S; ++i) {
+            const int col = s * S + i;
+            uc[col] = clampd(__dadd_rn(u[col], __dmul_rn(du[col], alpha)), -k.u_clamp, k.u_clamp);
+          }
+        CPMPC_GSYNC();
+        evaluate_errors<L>(c, P, w, xc, uc, x_cur, set_point, u_prev, step_f, step_eq);
+        CPMPC_GSYNC();
+        if (lrow != nullptr && c.gl == 0 && n_steps < 6) {
+          lrow[9 + 3 * n_steps] = alpha;
+          lrow[10 + 3 * n_steps] = step_f;
+          lrow[11 + 3 * n_steps] = step_eq;
+        }
+        ++n_steps;
+        const double phi = step_f + penalty * step_eq;
+        if (!isfinite(step_f) || !isfinite(step_eq)) {
+          step_result = SR_NON_FINITE;
+          ls_done = true;
+        } else if (linf < k.first_tol) {
+          step_result = SR_FIRST_ORDER;
+          ls_done = true;
+        } else if (dphi0 > 0.0) {
+          step_result = SR_POSITIVE_DERIVATIVE;
+          ls_done = true;
+        } else if (phi <= phi0 + dphi0 * alpha * k.armijo_c1) {
+          step_result = SR_SUCCESS;
+          ls_done = true;
+        } else {
+          a_prev2 = a_prev;
+          phi_prev2 = phi_prev;
+          a_prev = alpha;
+          phi_prev = phi;
+        }
+      }
+    }
+
+    // ---- lambda update and exit tests (nonlinear.cc:296-343) -------------------------------------------------------
+    if (active) {
+      bool exit_now = false;
+      if (step_result == SR_SUCCESS) {
+        for (int q = c.gl; q < NS; q += L) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) xs[4 * q + i] = xc[4 * q + i];
+        }
+        for (int s = c.gl; s < nseg; s += L)
+          for (int i = 0; i < S; ++i) u[s * S + i] = uc[s * S + i];
+        CPMPC_GSYNC();
+        lambda = fmax(lambda * ((opt_state == OS_RESTORE_LM) ? k.lam_dec_restore : k.lam_dec_success), k.lam_min);
+        opt_state = OS_NOMINAL;
+        cur_f = step_f;
+        cur_eq = step_eq;
+        if (fmax(step_f, step_eq) < k.abs_tol) {
+          res.termination = TS_ABS_TOL;
+          exit_now = true;
+        } else if (step_f + penalty * step_eq > phi0 * (1.0 - k.rel_tol)) {
+          res.termination = TS_REL_TOL;
+          exit_now = true;
+        }
+      } else if (step_result == SR_FIRST_ORDER) {
+        res.termination = TS_FIRST_ORDER;
+        exit_now = true;
+      } else if (step_result == SR_MAX_ITERATIONS || step_result == SR_POSITIVE_DERIVATIVE) {
+        if (opt_state == OS_NOMINAL) {
+          lambda = fmax(k.lam_fail_init, lambda * 10.0);
+          opt_state = OS_RESTORE_LM;
+        } else {
+          lambda *= 10.0;
+        }
+        if (lambda > k.lam_max) {
+          res.termination = TS_MAX_LAMBDA;
+          exit_now = true;
+        }
+      }
+      res.n_iter += 1;
+      res.n_ls += n_steps;
+      res.n_failed += (step_result != SR_SUCCESS && step_result != SR_FIRST_ORDER) ? 1 : 0;
+      res.last_step_result = step_result;
+      if (lrow != nullptr && c.gl == 0) {
+        lrow[0] = (double)opt_state;
+        lrow[1] = lambda_in;
+        lrow[2] = f0;
+        lrow[3] = eq0;
+        lrow[4] = d_f;
+        lrow[5] = d_eq;
+        lrow[6] = penalty;
+        lrow[7] = (double)step_result;
+        lrow[8] = (double)n_steps;
+      }
+      if (exit_now) active = false;
+    }
+  }
+  res.opt_state = opt_state;
+  res.f = cur_f;
+  res.eq = cur_eq;
+  res.penalty = penalty;
+  res.lambda = lambda;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Kernel: persistent grid-stride over instances; each warp carries 32/L instances at a time.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int L, int WARPS_PER_BLOCK>
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
+    cpmpc_solve_kernel(const KernelCfg cfg, const KernelIO io) {
+  extern __shared__ double smem[];
+  constexpr int G = 32 / L;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int g = lane / L;
+  Ctx c;
+  c.cfg = &cfg;
+  c.gl = lane % L;
+  c.gmask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << (g * L));
+  const long long group_id = ((long long)blockIdx.x * WARPS_PER_BLOCK + warp) * G + g;
+  const long long n_groups = (long long)gridDim.x * WARPS_PER_BLOCK * G;
+  c.sm = smem + (size_t)(warp * G + g) * cfg.stride;
+  c.lm = io.lm_scratch + (size_t)group_id * cfg.lm_stride;
+  const int W = cfg.W, S = cfg.S, NS = cfg.NS, N = cfg.N;
+  double* xs = c.sm + cfg.off_xs;
+  double* u = c.sm + cfg.off_u;
+
+  // every warp runs the same number of rounds so that warp-wide votes stay convergent
+  const long long rounds = (io.B + n_groups - 1) / n_groups;
+  for (long long round = 0; round < rounds; ++round) {
+    const long long inst = round * n_groups + group_id;
+    const bool have = inst < io.B;
+
+    DynConst P;
+    Weights w;
+    double x_cur[4] = {0.0, 0.0, 0.0, 0.0};
+    double set_point = 0.0;
+    if (have) {
+      P = make_dyn_const(io.dyn + inst * CPMPC_DYN_STRIDE);
+      if (io.weights != nullptr) {
+        const double* pw = io.weights + inst * CPMPC_WEIGHTS_STRIDE;
+        w.w_u = pw[0];
+        w.w_r = pw[1];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w.wt[i] = pw[2 + i];
+      } else {
+        w.w_u = cfg.w_u;
+        w.w_r = cfg.w_r;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w.wt[i] = cfg.wt[i];
+      }
+      if (!(w.w_u > 0.0)) w.w_u = 0.0;
+      if (!(w.w_r > 0.0)) w.w_r = 0.0;
+      const double* ps = (io.sim ? io.states_io : io.states) + inst * CPMPC_STATE_STRIDE;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x_cur[i] = ps[i];
+      set_point = io.set_points[inst];
+    } else {
+      P = DynConst{1.0, 2.0, 1.0, 1.0, 2.0, 2.0, 0.0, 0.0, 1.0, 0.0, 1.0, 9.81};
+      w.w_u = w.w_r = 1.0;
+      w.wt[0] = w.wt[1] = w.wt[2] = w.wt[3] = 1.0;
+    }
+
+    long long solves = 0, sum_iter = 0, sum_ls = 0, sum_bad = 0;
+    for (long long step = 0; step < io.n_steps; ++step) {
+      // ---- BuildProblem + initial guess (optimization.cc:44-71) ---------------------------------------------------
+      double u_prev = 0.0;
+      if (have) {
+        double* prev = io.prev + inst * N;
+        const bool warm = io.has_prev[inst] != 0;
+        if (warm) u_prev = prev[4 * NS];  // last step's applied control (optimization.cc:289-291)
+        for (int q = c.gl; q < W; q += L) {
+          u[q] = warm ? prev[4 * NS + ((q + 1 < W) ? q + 1 : q)] : io.u_guess[q];
+        }
+        CPMPC_GSYNC();
+        if (c.gl == 0) {
+          // FillInitialGuess: all shooting states re-integrated from x(0) (optimization.cc:333-351)
+          double x[4] = {x_cur[0], x_cur[1], x_cur[2], x_cur[3]};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) xs[i] = x[i];
+          for (int s = 1; s < NS; ++s) {
+            for (int i = 0; i < S; ++i) {
+              rk4_step<false>(P, x, u[(s - 1) * S + i], cfg.dt);
+              x[1] = mod_pi(x[1]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xs[4 * s + i] = x[i];
+          }
+        }
+        CPMPC_GSYNC();
+      }
+
+      SolveResult res;
+      double* ilog = (io.iter_log != nullptr && have)
+                         ? io.iter_log + (size_t)inst * cfg.max_iter * CPMPC_ITERLOG_STRIDE
+                         : nullptr;
+      solve_group<L>(c, have, P, w, x_cur, set_point, u_prev, ilog, res);
+
+      if (have) {
+        // ---- outputs (optimization.cc:83-96) ------------------------------------------------------------------
+        double* prev = io.prev + inst * N;
+        for (int q = c.gl; q < 4 * NS; q += L) prev[q] = xs[q];
+        for (int q = c.gl; q < W; q += L) {
+          prev[4 * NS + q] = u[q];
+          if (io.u_out != nullptr) io.u_out[inst * W + q] = u[q];
+        }
+        if (c.gl == 0) {
+          io.has_prev[inst] = 1;
+          if (io.pred_out != nullptr) {
+            // ComputePredictedStates (optimization.cc:353-371)
+            double x[4] = {x_cur[0], x_cur[1], x_cur[2], x_cur[3]};
+            double* po = io.pred_out + (size_t)inst * W * 4;
+            for (int q = 0; q < W; ++q) {
+              rk4_step<false>(P, x, u[q], cfg.dt);
+              x[1] = mod_pi(x[1]);
+              po[4 * q] = x[0];
+              po[4 * q + 1] = x[1];
+              po[4 * q + 2] = x[2];
+              po[4 * q + 3] = x[3];
+            }
+          }
+          if (io.stats != nullptr) {
+            cpmpc_stats st;
+            st.termination_state = res.termination;
+            st.n_iterations = res.n_iter;
+            st.n_line_search_steps = res.n_ls;
+            st.n_failed_line_searches = res.n_failed;
+            st.last_step_result = res.last_step_result;
+            st.optimizer_state = res.opt_state;
+            st.f = res.f;
+            st.equality = res.eq;
+            st.penalty = res.penalty;
+            st.lambda = res.lambda;
+            io.stats[inst] = st;
+          }
+          solves += 1;
+          sum_iter += res.n_iter;
+          sum_ls += res.n_ls;
+          sum_bad += (res.termination == TS_QP_INDEFINITE || res.termination == TS_MAX_LAMBDA ||
+                      res.termination == TS_REJECTED)
+                         ? 1
+                         : 0;
+          if (io.sim) {
+            // Simulator::Step(control_dt, u[0]) with 1 ms sub-steps (simulator.cc:11-36)
+            const double u0 = u[0];
+            if (io.controls_out != nullptr) io.controls_out[inst * io.n_steps + step] = u0;
+            double dt = cfg.dt;
+            double x[4] = {x_cur[0], x_cur[1], x_cur[2], x_cur[3]};
+            if (isfinite(u0)) {
+              while (dt > 0.0) {
+                rk4_step<false>(P, x, u0, fmin(dt, 0.001));
+                x[1] = mod_pi(x[1]);
+                dt -= 0.001;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x_cur[i] = x[i];
+          }
+        }
+        if (io.sim) {
+          const int src = (c.gmask == 0xffffffffu) ? 0 : (__ffs(c.gmask) - 1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) x_cur[i] = __shfl_sync(c.gmask, x_cur[i], src);
+        }
+        CPMPC_GSYNC();
+      }
+    }
+    if (have && c.gl == 0) {
+      if (io.sim) {
+        double* ps = io.states_io + inst * CPMPC_STATE_STRIDE;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ps[i] = x_cur[i];
+      }
+      if (io.stats_sum != nullptr) {
+        atomicAdd((unsigned long long*)&io.stats_sum[0], (unsigned long long)solves);
+        atomicAdd((unsigned long long*)&io.stats_sum[1], (unsigned long long)sum_iter);
+        atomicAdd((unsigned long long*)&io.stats_sum[2], (unsigned long long)sum_ls);
+        atomicAdd((unsigned long long*)&io.stats_sum[3], (unsigned long long)sum_bad);
+      }
+    }
+  }
+}
+
+#undef CPMPC_GSYNC
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Batched plant simulator: Simulator::Step (optimization/simulator.cc:11-36), one thread per plant.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void cpmpc_sim_kernel(const long long B, double* __restrict__ states, const double* __restrict__ dyn,
+                                 const double* __restrict__ u, const double dt_total,
+                                 const double* __restrict__ f_base, const double* __restrict__ f_mass) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const DynConst P = make_dyn_const(dyn + i * CPMPC_DYN_STRIDE);
+  double x[4] = {states[4 * i], states[4 * i + 1], states[4 * i + 2], states[4 * i + 3]};
+  const double ui = u[i];
+  const double fbx = f_base ? f_base[2 * i] : 0.0;
+  const double fmx = f_mass ? f_mass[2 * i] : 0.0;
+  const double fmy = f_mass ? f_mass[2 * i + 1] : 0.0;
+  double dt = dt_total;
+  while (dt > 0.0) {
+    rk4_step<true>(P, x, ui, fmin(dt, 0.001), fbx, fmx, fmy);
+    x[1] = mod_pi(x[1]);
+    dt -= 0.001;
+  }
+  states[4 * i] = x[0];
+  states[4 * i + 1] = x[1];
+  states[4 * i + 2] = x[2];
+  states[4 * i + 3] = x[3];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// FP64 FMA throughput probe: 8 independent register-resident DFMA chains per thread.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void cpmpc_dfma_probe_kernel(double* out, const int iters, const double a, const double b) {
+  double v0 = threadIdx.x * 1e-3, v1 = v0 + 1.0, v2 = v0 + 2.0, v3 = v0 + 3.0, v4 = v0 + 4.0, v5 = v0 + 5.0,
+         v6 = v0 + 6.0, v7 = v0 + 7.0;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      v0 = fma(v0, a, b);
+      v1 = fma(v1, a, b);
+      v2 = fma(v2, a, b);
+      v3 = fma(v3, a, b);
+      v4 = fma(v4, a, b);
+      v5 = fma(v5, a, b);
+      v6 = fma(v6, a, b);
+      v7 = fma(v7, a, b);
+    }
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+}
+
+}  // namespace cpmpc

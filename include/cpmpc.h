@@ -1,0 +1,164 @@
+/* cpmpc.h — C ABI of the B200-native batched cart-pole MPC solver (libcpmpc.so).
+ *
+ * This is the drop-in boundary for ONE hot path of gareth-cross/cart-pole-mpc: pendulum::Optimization::Step
+ * (optimization/optimization.cc:39-97) run over a batch of independent instances on one GPU.  The reference has no
+ * C ABI of its own; its boundary is the C++ class pendulum::Optimization (optimization/optimization.hpp:73-108) that
+ * the nanobind wrapper (wrapper/wrapper.cc:87-90) and optimization_test.cc call.  Each entry point below names the
+ * reference interface it replaces.  The C++ facade that keeps the reference's struct/class API on top of this ABI is
+ * cart_pole_mpc_b200/host/optimization.hpp; the Python mirror of `pypendulum` is cart_pole_mpc_b200/pypendulum.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no exceptions cross the ABI; every function returns a cpmpc_status
+ *     (0 = success) and cpmpc_last_error() returns a thread-local message for the last failure.
+ *   - all arrays are dense, row-major, FP64.  "B" is the batch size fixed at cpmpc_create().
+ *   - W = window_length, S = state_spacing, NS = W/S + 1, N = 4*NS + W (variable layout
+ *     [x(0) .. x(NS-1) | u(0) .. u(W-1)], optimization.cc:24-37).
+ *   - a handle is bound to one device; calls on one handle must be serialised by the caller (the reference object is
+ *     not thread safe either).  Use one handle per GPU for multi-GPU.
+ *   - there is NO CPU fallback: every call fails with CPMPC_ERR_CUDA when no usable device exists.
+ */
+#ifndef CPMPC_H_
+#define CPMPC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPMPC_VERSION 1
+
+typedef enum cpmpc_status {
+  CPMPC_OK = 0,
+  CPMPC_ERR_INVALID_ARGUMENT = 1, /* F_ASSERT-class precondition failures (optimization.cc:13-22) */
+  CPMPC_ERR_CUDA = 2,             /* CUDA runtime / launch failure, or no device */
+  CPMPC_ERR_UNSUPPORTED = 3,      /* problem shape outside what the kernels were built for */
+} cpmpc_status;
+
+/* pendulum::OptimizationParams (optimization/optimization.hpp:12-48), field for field, plus the handful of
+ * mini_opt solver parameters that Optimization::Step hard-codes (optimization.cc:73-79) so they stay visible. */
+typedef struct cpmpc_params {
+  double control_dt;                    /* 0.01 */
+  int64_t window_length;                /* 40 */
+  int64_t state_spacing;                /* 10 */
+  int64_t max_iterations;               /* 8 */
+  double relative_exit_tol;             /* 1e-5 */
+  double absolute_first_derivative_tol; /* 1e-6 */
+  double equality_penalty_initial;      /* 1.0 */
+  double u_guess_sinusoid_amplitude;    /* 10.0 */
+  double u_cost_weight;                 /* 0.1 */
+  double u_derivative_cost_weight;      /* 0.1 */
+  double b_x_final_cost_weight;         /* 150 */
+  double th_final_cost_weight;          /* -1 (negative => equality constraint) */
+  double b_x_dot_final_cost_weight;     /* -1 */
+  double th_dot_final_cost_weight;      /* -1 */
+} cpmpc_params;
+
+/* Per-instance solver statistics: the fields of mini_opt::NLSSolverOutputs / NLSIteration that callers read
+ * (dependencies/mini_opt/include/mini_opt/structs.hpp:277-347).  Enum values follow the reference declaration order. */
+typedef struct cpmpc_stats {
+  int32_t termination_state;      /* mini_opt::NLSTerminationState: 0 MAX_ITERATIONS, 1 SATISFIED_ABSOLUTE_TOL,
+                                     2 SATISFIED_RELATIVE_TOL, 3 SATISFIED_FIRST_ORDER_TOL, 4 MAX_LAMBDA,
+                                     5 QP_INDEFINITE; -1 = instance rejected (non-finite cost at the
+                                     linearisation point: the reference throws, nonlinear.cc:356-357) */
+  int32_t n_iterations;           /* solver_outputs.iterations.size() */
+  int32_t n_line_search_steps;    /* NLSSolverOutputs::NumLineSearchSteps() */
+  int32_t n_failed_line_searches; /* NLSSolverOutputs::NumFailedLineSearches() */
+  int32_t last_step_result;       /* mini_opt::StepSizeSelectionResult of the last iteration */
+  int32_t optimizer_state;        /* mini_opt::OptimizerState after the last iteration */
+  double f;                       /* Errors::f at the final variables (0.5 * sum of squared costs) */
+  double equality;                /* Errors::equality at the final variables (L1 norm) */
+  double penalty;                 /* final equality penalty mu */
+  double lambda;                  /* final Levenberg-Marquardt lambda */
+} cpmpc_stats;
+
+/* Layout of one record of the optional per-iteration log (doubles): optimizer_state, lambda (at entry),
+ * f(0), c(0), d_f, d_equality, penalty, step_result, n_steps, then 6 x (alpha, f, equality) — the fields of
+ * mini_opt::NLSIteration (structs.hpp:294-322).  The log holds max_iterations records per instance. */
+#define CPMPC_ITERLOG_STRIDE 27
+/* Per-instance cost-weight overrides: u, u_derivative, b_x_final, th_final, b_x_dot_final, th_dot_final. */
+#define CPMPC_WEIGHTS_STRIDE 6
+#define CPMPC_DYN_STRIDE 9   /* pendulum::SingleCartPoleParams, optimization/structs.hpp:8-26 */
+#define CPMPC_STATE_STRIDE 4 /* pendulum::SingleCartPoleState,  optimization/structs.hpp:44-49 */
+
+typedef struct cpmpc_solver* cpmpc_handle;
+
+/* Thread-local description of the last error returned on this thread ("" when none). */
+const char* cpmpc_last_error(void);
+int cpmpc_version(void);
+
+/* OptimizationParams{} defaults (optimization.hpp:12-48). */
+void cpmpc_default_params(cpmpc_params* params);
+
+/* Replaces `Optimization::Optimization(const OptimizationParams&)` (optimization.cc:13-22) for `batch` independent
+ * controllers on CUDA device `device`.  Validates the same preconditions. */
+int cpmpc_create(const cpmpc_params* params, int64_t batch, int device, cpmpc_handle* out);
+int cpmpc_destroy(cpmpc_handle h);
+
+/* Problem dimensions derived from the params of a handle. */
+int64_t cpmpc_batch(cpmpc_handle h);
+int64_t cpmpc_solution_dim(cpmpc_handle h); /* N */
+
+/* Replaces `Optimization::Step` (optimization.cc:39-97) for all B instances, HOST buffers, synchronous.
+ *   states      [B*4]   current states          dyn_params [B*9]   dynamics parameters
+ *   set_points  [B]     b_x set points          weights    [B*6] or NULL (use params)
+ *   u_out       [B*W]   OptimizationOutputs::u
+ *   pred_out    [B*W*4] OptimizationOutputs::predicted_states, or NULL to skip computing them
+ *   stats_out   [B]     or NULL
+ * Warm-start state (Optimization::previous_solution_) is kept on the device inside the handle. */
+int cpmpc_step(cpmpc_handle h, const double* states, const double* dyn_params, const double* set_points,
+               const double* weights, double* u_out, double* pred_out, cpmpc_stats* stats_out);
+
+/* Same, with DEVICE pointers (on the handle's device), asynchronous on `stream` (a cudaStream_t, may be NULL for
+ * the default stream).  The caller synchronises. */
+int cpmpc_step_device(cpmpc_handle h, const double* states, const double* dyn_params, const double* set_points,
+                      const double* weights, double* u_out, double* pred_out, cpmpc_stats* stats_out,
+                      void* stream);
+
+/* Replaces `Optimization::Reset()` (optimization.hpp:83).  mask: HOST [B] bytes, non-zero = reset; NULL = all. */
+int cpmpc_reset(cpmpc_handle h, const uint8_t* mask);
+
+/* Replaces `Optimization::SetPreviousSolution` (optimization.hpp:86-89).  solutions: HOST [B*N].
+ * mask: HOST [B] (non-zero = set), NULL = all. */
+int cpmpc_set_previous_solution(cpmpc_handle h, const double* solutions, const uint8_t* mask);
+
+/* Reads back the warm-start buffer (what OptimizationOutputs::previous_solution will be on the NEXT Step,
+ * optimization.cc:84-85).  solutions_out: HOST [B*N]; has_prev_out: HOST [B] or NULL. */
+int cpmpc_get_previous_solution(cpmpc_handle h, double* solutions_out, uint8_t* has_prev_out);
+
+/* Enables (1) / disables (0) the per-iteration log (NLSIteration records); off by default. */
+int cpmpc_enable_iteration_log(cpmpc_handle h, int enable);
+/* Copies the log of the last Step to HOST log_out [B * max_iterations * CPMPC_ITERLOG_STRIDE]. */
+int cpmpc_get_iteration_log(cpmpc_handle h, double* log_out);
+
+/* Replaces `Simulator::Step` (optimization/simulator.cc:11-23) for B plants, DEVICE pointers, async on `stream`.
+ *   states [B*4] in/out, dyn_params [B*9], u [B], f_base/f_mass [B*2] or NULL (zero forces). */
+int cpmpc_sim_step_device(int64_t batch, double* states, const double* dyn_params, const double* u, double dt,
+                          const double* f_base, const double* f_mass, void* stream);
+/* HOST-buffer variant of the above on CUDA device `device`, synchronous. */
+int cpmpc_sim_step(int device, int64_t batch, double* states, const double* dyn_params, const double* u, double dt,
+                   const double* f_base, const double* f_mass);
+
+/* Closed loop of `n_steps` x { Step(states); Simulator::Step(control_dt, u[0]) } entirely on the device
+ * (the loop of optimization_test.cc:38-61 / viz/src/application.ts:424-458), HOST buffers, synchronous.
+ *   states [B*4] in/out; controls_out [B*n_steps] or NULL; stats_sum_out[4] or NULL receives
+ *   {solves, sqp iterations, line-search steps, solves ending QP_INDEFINITE|MAX_LAMBDA|rejected}. */
+int cpmpc_closed_loop(cpmpc_handle h, int64_t n_steps, double* states, const double* dyn_params,
+                      const double* set_points, const double* weights, double* controls_out,
+                      int64_t* stats_sum_out);
+/* DEVICE-pointer variant, asynchronous on `stream`; stats_sum (device int64[4]) is accumulated into. */
+int cpmpc_closed_loop_device(cpmpc_handle h, int64_t n_steps, double* states, const double* dyn_params,
+                             const double* set_points, const double* weights, double* controls_out,
+                             int64_t* stats_sum, void* stream);
+
+/* Number of kernel launches issued by this library since load (for bench accounting). */
+int64_t cpmpc_launch_count(void);
+
+/* Measures the FP64 FMA throughput of the device with a register-resident DFMA chain microkernel and returns
+ * it in *tflops_out (2 flops per FMA).  Used as the roofline denominator (MEASURED_PEAKS.json has no FP64 entry). */
+int cpmpc_measure_fp64_peak(int device, double* tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPMPC_H_ */
