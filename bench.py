@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched cold-start swing-up MPC solves (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--allgather]
+
+One "step" = one pass of Optimization::Step over a batch of B = 4096 synthetic instances per GPU (randomised
+initial states and cart/pole masses, cold start: the warm start is reset before every step).  Under torchrun
+(N > 1) every rank owns its own 4096 instances (weak scaling, no data-path collective).  Rank 0 prints ONE JSON
+line; see README / DESIGN.md for the meaning of each key.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "batched MPC solves/sec (FP64), cold-start swing-up"
+UNIT = "solves/s"
+DEFAULT_BATCH = 4096
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Algorithmic flop count of one solve, SURVEY.md section 8(d) (FMA = 2 flops, sin/cos/tanh/sqrt/div/fmod = 1 flop).
+# ----------------------------------------------------------------------------------------------------------------------
+def algorithmic_flops(n_iter, n_ls, W=40, S=10, n_te=3, n_cost=81):
+    nx = 4
+    NS = W // S + 1
+    N = nx * NS + W
+    K = nx * (NS - 1) + nx + n_te
+    C_fJ, C_f = 198, 76
+    C_rkJ = 4 * C_fJ + 710
+    C_rk = 4 * C_f + 60
+    C_bwd = 140
+    F_lin = W * (C_rkJ + C_bwd) + 6 * n_cost
+    F_merit = W * C_rk + 3 * n_cost + 2 * K
+    F_roll = W * C_rk
+    F_dir = 2 * K * N + 2 * N * N + 4 * N
+    F_qp = W ** 3 / 3 + 2 * W * W * (n_te + 2) + 2 * nx * nx * W * (NS - 1) + 2 * nx * NS * W
+    return n_iter * (F_lin + F_qp + F_dir) + n_ls * F_merit + 2 * F_roll
+
+
+def hbm_bytes_per_solve(W=40, S=10):
+    """Algorithmic HBM traffic of one solve: inputs + warm start in, results + new warm start out."""
+    NS = W // S + 1
+    N = 4 * NS + W
+    return (32 + 72 + 8 + 8 * W) + (8 * W + 32 * W + 8 * N + 56)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Clock sampling during the timed region (B200_PROFILING.md)
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+
+        def pump():
+            for line in self.proc.stdout:
+                self.lines.append(line.strip())
+
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(smax)) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (a port of the reference's CPU algorithm; the reference itself needs Eigen and cannot be
+# built here), one instance per OpenMP thread over all host cores.
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_baseline(states, dyn, sp, repeats=3, n_threads=0):
+    from oracle import oracle_py
+    opt = oracle_py.opt_array()
+    best = None
+    result = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        result = oracle_py.batch_step(opt, states, dyn, sp, n_threads=n_threads, want_iter_log=False)
+        dt = time.perf_counter() - t0
+        best = dt if best is None or dt < best else best
+    return result, best
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port) on the host cores, same metric and config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from cart_pole_mpc_b200 import synthetic
+    from oracle import oracle_py
+    B = args.batch
+    states, dyn, sp = synthetic.swingup_batch(B)
+    opt = oracle_py.opt_array()
+    threads = 0
+    for _ in range(args.warmup):
+        threads = oracle_py.batch_step(opt, states[:256], dyn[:256], sp[:256], want_iter_log=False).threads
+    times = []
+    res = None
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        res = oracle_py.batch_step(opt, states, dyn, sp, want_iter_log=False)
+        times.append(time.perf_counter() - t0)
+        threads = res.threads
+    total = float(np.sum(times))
+    value = B * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{B}-instance batched cold-start swing-up solves, W=40 S=10 max_iter=8, randomized "
+                               "initial states and cart/pole masses (BASELINE.json configs[1]); CPU, one instance "
+                               "per thread"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{B} instances x {args.steps} passes (the full step workload)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "mean_sqp_iterations": float(res.n_iterations.mean()), "mean_merit_evaluations": float(res.n_line_search.mean()),
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=DEFAULT_BATCH, help="instances per GPU")
+    ap.add_argument("--allgather", action="store_true",
+                    help="also all-gather u and stats across ranks inside the timed region (NCCL)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        if args.steps > 20:
+            args.steps = 20  # bounded so the CPU arm ends within a couple of minutes
+        if args.warmup > 3:
+            args.warmup = 3
+        return run_reference(args)
+
+    import torch
+    from cart_pole_mpc_b200 import BatchedOptimization, measure_fp64_peak, launch_count, synthetic, _capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    B = args.batch
+    W, S = 40, 10
+    states_h, dyn_h, sp_h = synthetic.swingup_batch(B, first=rank * B)
+    solver = BatchedOptimization(B, device=local_rank)
+
+    # ---- device-resident arm (`value`) -----------------------------------------------------------------------------
+    states_d = torch.from_numpy(states_h).to(dev)
+    dyn_d = torch.from_numpy(dyn_h).to(dev)
+    sp_d = torch.from_numpy(sp_h).to(dev)
+    u_d = torch.empty((B, W), dtype=torch.float64, device=dev)
+    pred_d = torch.empty((B, W, 4), dtype=torch.float64, device=dev)
+    stats_d = torch.empty((B, 56), dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # 256 MiB > 126 MB L2
+
+    gathered_u = gathered_stats = None
+    if dist is not None and args.allgather:
+        gathered_u = torch.empty((world * B, W), dtype=torch.float64, device=dev)
+        gathered_stats = torch.empty((world * B, 56), dtype=torch.uint8, device=dev)
+
+    def one_step():
+        solver.reset_device()  # cold start every step (async memset on the same stream)
+        solver.step_device(states_d, dyn_d, sp_d, u_d, pred_out=pred_d, stats_out=stats_d)
+        if gathered_u is not None:
+            dist.all_gather_into_tensor(gathered_u, u_d)
+            dist.all_gather_into_tensor(gathered_stats, stats_d)
+
+    for _ in range(max(args.warmup, 3)):
+        flush.fill_(1)
+        one_step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = launch_count()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)  # L2 flush between timed iterations (not timed)
+        starts[i].record()
+        one_step()
+        stops[i].record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    launches = launch_count() - launches0
+    step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, stops)])
+    total_ms = float(step_ms.sum())
+    clocks = sampler.stop() if rank == 0 else None
+
+    stats = np.frombuffer(stats_d.cpu().numpy().tobytes(), dtype=_capi.STATS_DTYPE)
+    n_iter_sum = float(stats["n_iterations"].sum())
+    n_ls_sum = float(stats["n_line_search_steps"].sum())
+    flops_step = float(algorithmic_flops(stats["n_iterations"].astype(np.float64),
+                                         stats["n_line_search_steps"].astype(np.float64)).sum())
+
+    # ---- end-to-end arm (`e2e`): the C-ABI host-buffer call, pinned host memory, H2D + kernel + D2H per step -----------
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    st_p, dy_p, sp_p = pin(states_h), pin(dyn_h), pin(sp_h)
+    u_p = torch.empty((B, W), dtype=torch.float64).pin_memory()
+    pred_p = torch.empty((B, W, 4), dtype=torch.float64).pin_memory()
+    stats_p = torch.empty((B, 56), dtype=torch.uint8).pin_memory()
+    lib = _capi.lib()
+
+    def one_e2e():
+        _capi.check(lib.cpmpc_reset_device(solver._h, None))
+        _capi.check(lib.cpmpc_step(solver._h, st_p.data_ptr(), dy_p.data_ptr(), sp_p.data_ptr(), None,
+                                   u_p.data_ptr(), pred_p.data_ptr(), stats_p.data_ptr()))
+
+    e2e_steps = max(10, args.steps // 4)
+    for _ in range(3):
+        one_e2e()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        one_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d = B * (4 + 9 + 1) * 8
+    d2h = B * (W + 4 * W) * 8 + B * 56
+
+    # ---- single-solve latency through the same boundary (batch of 1, host buffers) ------------------------------------
+    lat = None
+    if rank == 0:
+        one = BatchedOptimization(1, device=local_rank)
+        s1, d1, p1 = states_h[:1].copy(), dyn_h[:1].copy(), sp_h[:1].copy()
+        ts = []
+        for i in range(60):
+            one.reset()
+            t0 = time.perf_counter()
+            one.step(s1, d1, p1)
+            ts.append(time.perf_counter() - t0)
+        lat = {"p50_ms": float(np.percentile(ts[10:], 50) * 1e3), "p99_ms": float(np.percentile(ts[10:], 99) * 1e3),
+               "batch": 1, "path": "cpmpc_step (host buffers)"}
+        one.close()
+
+    # ---- reduce over ranks: max time, summed work -----------------------------------------------------------------
+    if dist is not None:
+        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s = float(t[0]), float(t[1])
+        w = torch.tensor([flops_step, n_iter_sum, n_ls_sum], dtype=torch.float64, device=dev)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        flops_step_all = float(w[0])
+    else:
+        flops_step_all = flops_step
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    value = world * B * args.steps / (total_ms * 1e-3)
+    e2e_value = world * B * e2e_steps / e2e_s
+    peak_tflops = measure_fp64_peak(local_rank)
+    kernel_ms = total_ms / args.steps
+    achieved_tflops = flops_step / (kernel_ms * 1e-3) / 1e12  # per GPU: this rank's flops over the max step time
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_achieved = B * hbm_bytes_per_solve(W, S) / (kernel_ms * 1e-3) / 1e9
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"{B}-instance batched cold-start swing-up solves per GPU, W=40 S=10 max_iter=8, "
+                               "randomized initial states and cart/pole masses (BASELINE.json configs[1])",
+                   "batch_per_gpu": B, "l2": "flushed between timed steps (256 MiB write, untimed)",
+                   "outputs": "u, predicted_states and solver stats all computed every step",
+                   "allgather": bool(gathered_u is not None)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "path": "cpmpc_step: pinned host buffers -> H2D -> kernel -> D2H"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
+                     "frac": achieved_tflops / peak_tflops if peak_tflops else None, "traffic": None,
+                     "peak_source": "DFMA microkernel measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                     "flops_model": "SURVEY.md 8(d) algorithmic count from the solver's own n_iter / n_ls counters",
+                     "flops_per_solve": flops_step / B,
+                     "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": hbm_achieved / hbm_peak,
+                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
+        "latency": lat,
+        "wall_seconds_timed_region": t_wall,
+        "mean_sqp_iterations": n_iter_sum / B, "mean_merit_evaluations": n_ls_sum / B,
+        "step_ms_min_median_max": [float(step_ms.min()), float(np.median(step_ms)), float(step_ms.max())],
+        "aggregate_algorithmic_tflops": flops_step_all / (kernel_ms * 1e-3) / 1e12,
+    }
+
+    if not args.no_cpu_baseline and world == 1:
+        res, best = cpu_baseline(states_h, dyn_h, sp_h, repeats=3)
+        line["cpu_baseline"] = {"value": B / best, "unit": UNIT, "cores": res.threads, "kind": "port",
+                                "sample": f"the same {B} instances, best of 3 passes, one instance per thread"}
+        # parity of this very run against the oracle
+        g_merit = stats["f"] + stats["penalty"] * stats["equality"]
+        rel = np.abs(g_merit - res.merit) / np.maximum(np.abs(res.merit), 1e-300)
+        u_gpu = u_d.cpu().numpy()
+        line["parity"] = {
+            "frac_within_1e-8_rel_cost": float((rel <= 1e-8).mean()),
+            "iteration_count_match": float((stats["n_iterations"] == res.n_iterations).mean()),
+            "termination_match": float((stats["termination_state"] == res.termination).mean()),
+            "median_abs_du": float(np.median(np.abs(u_gpu - res.u).max(axis=1))),
+        }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

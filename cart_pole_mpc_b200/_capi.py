@@ -14,7 +14,8 @@ WEIGHTS_STRIDE = 6
 # every symbol include/cpmpc.h declares
 EXPORTED_SYMBOLS = (
     "cpmpc_last_error", "cpmpc_version", "cpmpc_default_params", "cpmpc_create", "cpmpc_destroy", "cpmpc_batch",
-    "cpmpc_solution_dim", "cpmpc_step", "cpmpc_step_device", "cpmpc_reset", "cpmpc_set_previous_solution",
+    "cpmpc_solution_dim", "cpmpc_step", "cpmpc_step_device", "cpmpc_reset", "cpmpc_reset_device",
+    "cpmpc_set_previous_solution",
     "cpmpc_get_previous_solution", "cpmpc_enable_iteration_log", "cpmpc_get_iteration_log", "cpmpc_sim_step_device",
     "cpmpc_sim_step", "cpmpc_closed_loop", "cpmpc_closed_loop_device", "cpmpc_launch_count",
     "cpmpc_measure_fp64_peak",
@@ -42,7 +43,7 @@ class CpmpcParams(C.Structure):
 
 
 class CpmpcStats(C.Structure):
-    """struct cpmpc_stats (64 bytes)."""
+    """struct cpmpc_stats (56 bytes)."""
     _fields_ = [
         ("termination_state", C.c_int32),
         ("n_iterations", C.c_int32),
@@ -101,6 +102,8 @@ def lib() -> C.CDLL:
     L.cpmpc_step_device.argtypes = [vp] * 9
     L.cpmpc_reset.restype = C.c_int
     L.cpmpc_reset.argtypes = [vp, vp]
+    L.cpmpc_reset_device.restype = C.c_int
+    L.cpmpc_reset_device.argtypes = [vp, vp]
     L.cpmpc_set_previous_solution.restype = C.c_int
     L.cpmpc_set_previous_solution.argtypes = [vp, vp, vp]
     L.cpmpc_get_previous_solution.restype = C.c_int

@@ -155,6 +155,12 @@ class BatchedOptimization:
             raise ValueError("mask must have shape (batch,)")
         _capi.check(self._lib.cpmpc_reset(self._h, m.ctypes.data if m is not None else None))
 
+    def reset_device(self, stream=None) -> None:
+        """Asynchronous Reset() of all instances on `stream` (torch stream or None for the current one)."""
+        import torch
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        _capi.check(self._lib.cpmpc_reset_device(self._h, s.cuda_stream))
+
     def set_previous_solution(self, solutions, mask=None) -> None:
         sol = _host(solutions, (self.batch, self.N), "solutions")
         m = np.ascontiguousarray(np.asarray(mask, dtype=np.uint8)) if mask is not None else None

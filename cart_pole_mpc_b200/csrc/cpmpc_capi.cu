@@ -46,7 +46,8 @@ struct cpmpc_solver {
   long long B = 0;
   int device = 0;
   int lanes = 1;   // L: lanes per instance
-  int grid = 0;    // persistent grid (1 warp per block)
+  int grid = 0;    // persistent grid, in blocks
+  int warps_per_block = 1;
   size_t smem_bytes = 0;
   KernelCfg cfg;
   cudaStream_t stream = nullptr;
@@ -76,12 +77,12 @@ using KernelFn = void (*)(const KernelCfg, const KernelIO);
 
 KernelFn SelectKernel(int lanes) {
   switch (lanes) {
-    case 1: return cpmpc_solve_kernel<1, 1>;
-    case 2: return cpmpc_solve_kernel<2, 1>;
-    case 4: return cpmpc_solve_kernel<4, 1>;
-    case 8: return cpmpc_solve_kernel<8, 1>;
-    case 16: return cpmpc_solve_kernel<16, 1>;
-    default: return cpmpc_solve_kernel<32, 1>;
+    case 1: return cpmpc_solve_kernel<1>;
+    case 2: return cpmpc_solve_kernel<2>;
+    case 4: return cpmpc_solve_kernel<4>;
+    case 8: return cpmpc_solve_kernel<8>;
+    case 16: return cpmpc_solve_kernel<16>;
+    default: return cpmpc_solve_kernel<32>;
   }
 }
 
@@ -96,8 +97,6 @@ void BuildLayout(KernelCfg& k) {
   const int W = k.W, NS = k.NS, nseg = k.nseg;
   k.off_xs = take(4 * NS);
   k.off_u = take(W);
-  k.off_xc = take(4 * NS);
-  k.off_uc = take(W);
   k.off_dxs = take(4 * NS);
   k.off_du = take(W);
   k.off_phi = take(16 * nseg);
@@ -105,6 +104,10 @@ void BuildLayout(KernelCfg& k) {
   k.off_gam = take(4 * W);
   k.off_gdu = take(4 * nseg);
   k.off_M = take(4 * W);
+  // the line-search candidates are only live after the QP has been solved: they alias the QP's U rows
+  k.off_xc = k.off_M;
+  k.off_uc = k.off_M + 4 * NS;
+  if (4 * NS + W > 4 * W) take(4 * NS + W - 4 * W);
   k.off_Y = take(5 * W);
   k.off_tl = take(W);
   k.off_tinv = take(W);
@@ -127,7 +130,7 @@ int Launch(cpmpc_solver* h, KernelIO io, cudaStream_t stream) {
   io.has_prev = h->d_has_prev;
   io.lm_scratch = h->d_lm;
   io.iter_log = h->log_enabled ? h->d_iter_log : nullptr;
-  fn<<<h->grid, 32, h->smem_bytes, stream>>>(h->cfg, io);
+  fn<<<h->grid, 32 * h->warps_per_block, h->smem_bytes, stream>>>(h->cfg, io);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return CPMPC_OK;
@@ -252,29 +255,40 @@ int cpmpc_create(const cpmpc_params* params, int64_t batch, int device, cpmpc_ha
   }
   h->lanes = lanes;
   const int groups_per_warp = 32 / lanes;
-  h->smem_bytes = sizeof(double) * static_cast<size_t>(k.stride) * groups_per_warp;
+  const size_t smem_per_warp = sizeof(double) * static_cast<size_t>(k.stride) * groups_per_warp;
 
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-  if (h->smem_bytes > static_cast<size_t>(prop.sharedMemPerBlockOptin)) {
+  if (smem_per_warp > static_cast<size_t>(prop.sharedMemPerBlockOptin)) {
     delete h;
-    return Fail(CPMPC_ERR_UNSUPPORTED, "problem needs " + std::to_string(h->smem_bytes) +
+    return Fail(CPMPC_ERR_UNSUPPORTED, "problem needs " + std::to_string(smem_per_warp) +
                                            " bytes of shared memory per warp, device offers " +
                                            std::to_string(prop.sharedMemPerBlockOptin));
   }
+  // Up to 4 warps per block so that the warps of one block sit on the 4 sub-partitions of an SM (a block of ONE warp
+  // lets several blocks pile onto the same sub-partition and serialise on its FP64 pipe).
+  int wpb = 4;
+  if (const char* env = std::getenv("CPMPC_WARPS_PER_BLOCK")) {
+    const int v = std::atoi(env);
+    if (v == 1 || v == 2 || v == 4) wpb = v;
+  }
+  while (wpb > 1 && smem_per_warp * wpb > static_cast<size_t>(prop.sharedMemPerBlockOptin)) wpb >>= 1;
+  h->warps_per_block = wpb;
+  h->smem_bytes = smem_per_warp * wpb;
   KernelFn fn = SelectKernel(lanes);
   CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->smem_bytes)));
   int blocks_per_sm = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, 32, h->smem_bytes));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, 32 * wpb, h->smem_bytes));
   if (blocks_per_sm < 1) {
     delete h;
     return Fail(CPMPC_ERR_UNSUPPORTED, "kernel does not fit on an SM");
   }
-  const long long warps_needed = (batch + groups_per_warp - 1) / groups_per_warp;
+  const long long groups_per_block = static_cast<long long>(groups_per_warp) * wpb;
+  const long long blocks_needed = (batch + groups_per_block - 1) / groups_per_block;
   const long long resident = static_cast<long long>(blocks_per_sm) * prop.multiProcessorCount;
-  h->grid = static_cast<int>(warps_needed < resident ? warps_needed : resident);
+  h->grid = static_cast<int>(blocks_needed < resident ? blocks_needed : resident);
 
-  const long long n_groups = static_cast<long long>(h->grid) * groups_per_warp;
+  const long long n_groups = static_cast<long long>(h->grid) * groups_per_block;
   CUDA_TRY(cudaMalloc(&h->d_prev, sizeof(double) * batch * k.N));
   CUDA_TRY(cudaMalloc(&h->d_has_prev, batch));
   CUDA_TRY(cudaMemset(h->d_has_prev, 0, batch));
@@ -387,6 +401,13 @@ int cpmpc_reset(cpmpc_handle h, const uint8_t* mask) {
     if (mask[i]) flags[i] = 0;
   }
   CUDA_TRY(cudaMemcpy(h->d_has_prev, flags.data(), h->B, cudaMemcpyHostToDevice));
+  return CPMPC_OK;
+}
+
+int cpmpc_reset_device(cpmpc_handle h, void* stream) {
+  if (h == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemsetAsync(h->d_has_prev, 0, h->B, static_cast<cudaStream_t>(stream)));
   return CPMPC_OK;
 }
 

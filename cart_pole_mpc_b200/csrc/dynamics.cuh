@@ -186,137 +186,108 @@ __device__ __forceinline__ void dyn_eval_jac(const DynConst& P, const double b_x
   fth[3] = inv_det * (P.m_over_l2 * dw_th_k + dq_x_dw * s_m1_over_l);
 }
 
-// One classic RK4 step, in place, no Jacobians (integration.hpp:53-62).
+// One classic RK4 step, in place, no Jacobians (integration.hpp:53-62).  The four stages run as a rolled loop around
+// ONE inlined copy of the dynamics so the hot code stays inside the instruction cache.
 template <bool FORCES>
 __device__ __forceinline__ void rk4_step(const DynConst& P, double x[4], const double u, const double h,
                                          const double fb_x = 0.0, const double fm_x = 0.0, const double fm_y = 0.0) {
   const double hh = h * 0.5;
-  double a1x, a1t, a2x, a2t, a3x, a3t, a4x, a4t;
-  dyn_eval<FORCES>(P, x[0], x[1], x[2], x[3], u, fb_x, fm_x, fm_y, a1x, a1t);
-  const double v2x = x[2] + a1x * hh, v2t = x[3] + a1t * hh;
-  dyn_eval<FORCES>(P, x[0] + x[2] * hh, x[1] + x[3] * hh, v2x, v2t, u, fb_x, fm_x, fm_y, a2x, a2t);
-  const double v3x = x[2] + a2x * hh, v3t = x[3] + a2t * hh;
-  dyn_eval<FORCES>(P, x[0] + v2x * hh, x[1] + v2t * hh, v3x, v3t, u, fb_x, fm_x, fm_y, a3x, a3t);
-  const double v4x = x[2] + a3x * h, v4t = x[3] + a3t * h;
-  dyn_eval<FORCES>(P, x[0] + v3x * h, x[1] + v3t * h, v4x, v4t, u, fb_x, fm_x, fm_y, a4x, a4t);
-  const double h6 = h / 6.0;
-  const double n0 = x[0] + h6 * (x[2] + v2x * 2.0 + v3x * 2.0 + v4x);
-  const double n1 = x[1] + h6 * (x[3] + v2t * 2.0 + v3t * 2.0 + v4t);
-  const double n2 = x[2] + h6 * (a1x + a2x * 2.0 + a3x * 2.0 + a4x);
-  const double n3 = x[3] + h6 * (a1t + a2t * 2.0 + a3t * 2.0 + a4t);
-  x[0] = n0;
-  x[1] = n1;
-  x[2] = n2;
-  x[3] = n3;
-}
-
-// K (4x4, row-major) = F * P where F = [[0 0 1 0],[0 0 0 1],[fx],[fth]].
-__device__ __forceinline__ void stage_mul(const double fx[4], const double fth[4], const double Pm[16], double K[16]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    K[j] = Pm[8 + j];
-    K[4 + j] = Pm[12 + j];
-    K[8 + j] = fx[0] * Pm[j] + fx[1] * Pm[4 + j] + fx[2] * Pm[8 + j] + fx[3] * Pm[12 + j];
-    K[12 + j] = fth[0] * Pm[j] + fth[1] * Pm[4 + j] + fth[2] * Pm[8 + j] + fth[3] * Pm[12 + j];
+  double a0 = x[0], a1 = x[1], a2 = x[2], a3 = x[3];  // stage argument
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;      // k1 + 2 k2 + 2 k3 + k4
+#pragma unroll 1
+  for (int st = 0; st < 4; ++st) {
+    double ax, at;
+    dyn_eval<FORCES>(P, a0, a1, a2, a3, u, fb_x, fm_x, fm_y, ax, at);
+    const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
+    s0 += a2 * wgt;
+    s1 += a3 * wgt;
+    s2 += ax * wgt;
+    s3 += at * wgt;
+    const double cst = (st == 2) ? h : hh;
+    const double n0 = x[0] + a2 * cst, n1 = x[1] + a3 * cst, n2 = x[2] + ax * cst, n3 = x[3] + at * cst;
+    a0 = n0;
+    a1 = n1;
+    a2 = n2;
+    a3 = n3;
   }
+  const double h6 = h / 6.0;
+  x[0] += h6 * s0;
+  x[1] += h6 * s1;
+  x[2] += h6 * s2;
+  x[3] += h6 * s3;
 }
 
 // One RK4 step with the Jacobians of the step map (integration.hpp:13-49): x is advanced in place,
-// A = d x+ / d x (4x4 row-major), Bv = d x+ / d u.
+// A = d x+ / d x (4x4 row-major), Bv = d x+ / d u.  Stage Jacobians have the structure
+// F = [[0 0 1 0],[0 0 0 1],[fx],[fth]], Fu = [0 0 gx gth]; the chain rule K_i = F_i (I + c_i K_{i-1}) and
+// ku_i = F_i ku_{i-1} c_i + Fu_i is carried through a rolled stage loop.
 __device__ __forceinline__ void rk4_step_jac(const DynConst& P, double x[4], const double u, const double h,
                                              double A[16], double Bv[4]) {
   const double hh = h * 0.5;
-  double fx[4], fth[4], gx, gth;
-  double K[16], Pm[16];
-  double ku[4], kun[4];
-
-  // stage 1
-  double a1x, a1t;
-  dyn_eval_jac(P, x[0], x[1], x[2], x[3], u, a1x, a1t, fx, fth, gx, gth);
-  // K1 = F1 (structured); accumulate A = K1, build P = I + K1 * h/2
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    K[j] = (j == 2) ? 1.0 : 0.0;
-    K[4 + j] = (j == 3) ? 1.0 : 0.0;
-    K[8 + j] = fx[j];
-    K[12 + j] = fth[j];
-  }
+  double a0 = x[0], a1 = x[1], a2 = x[2], a3 = x[3];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  double K[16], ku[4];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    A[i] = K[i];
-    Pm[i] = ((i % 5 == 0) ? 1.0 : 0.0) + K[i] * hh;
-  }
-  ku[0] = 0.0;
-  ku[1] = 0.0;
-  ku[2] = gx;
-  ku[3] = gth;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) Bv[i] = ku[i];
-
-  // stage 2
-  const double v2x = x[2] + a1x * hh, v2t = x[3] + a1t * hh;
-  double a2x, a2t;
-  dyn_eval_jac(P, x[0] + x[2] * hh, x[1] + x[3] * hh, v2x, v2t, u, a2x, a2t, fx, fth, gx, gth);
-  stage_mul(fx, fth, Pm, K);
-  kun[0] = ku[2] * hh;
-  kun[1] = ku[3] * hh;
-  kun[2] = (fx[0] * ku[0] + fx[1] * ku[1] + fx[2] * ku[2] + fx[3] * ku[3]) * hh + gx;
-  kun[3] = (fth[0] * ku[0] + fth[1] * ku[1] + fth[2] * ku[2] + fth[3] * ku[3]) * hh + gth;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    A[i] += K[i] * 2.0;
-    Pm[i] = ((i % 5 == 0) ? 1.0 : 0.0) + K[i] * hh;
+    K[i] = 0.0;
+    A[i] = 0.0;
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    ku[i] = kun[i];
-    Bv[i] += ku[i] * 2.0;
+    ku[i] = 0.0;
+    Bv[i] = 0.0;
   }
-
-  // stage 3
-  const double v3x = x[2] + a2x * hh, v3t = x[3] + a2t * hh;
-  double a3x, a3t;
-  dyn_eval_jac(P, x[0] + v2x * hh, x[1] + v2t * hh, v3x, v3t, u, a3x, a3t, fx, fth, gx, gth);
-  stage_mul(fx, fth, Pm, K);
-  kun[0] = ku[2] * hh;
-  kun[1] = ku[3] * hh;
-  kun[2] = (fx[0] * ku[0] + fx[1] * ku[1] + fx[2] * ku[2] + fx[3] * ku[3]) * hh + gx;
-  kun[3] = (fth[0] * ku[0] + fth[1] * ku[1] + fth[2] * ku[2] + fth[3] * ku[3]) * hh + gth;
+  double cprev = 0.0;  // coefficient that multiplied the previous stage's k in this stage's argument
+#pragma unroll 1
+  for (int st = 0; st < 4; ++st) {
+    double ax, at, fx[4], fth[4], gx, gth;
+    dyn_eval_jac(P, a0, a1, a2, a3, u, ax, at, fx, fth, gx, gth);
+    // Pm = I + K_prev * cprev  (identity at stage 0 because cprev = 0 and K = 0)
+    double Pm[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    A[i] += K[i] * 2.0;
-    Pm[i] = ((i % 5 == 0) ? 1.0 : 0.0) + K[i] * h;
-  }
+    for (int i = 0; i < 16; ++i) Pm[i] = ((i % 5 == 0) ? 1.0 : 0.0) + K[i] * cprev;
+    // K = F * Pm
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    ku[i] = kun[i];
-    Bv[i] += ku[i] * 2.0;
+    for (int j = 0; j < 4; ++j) {
+      K[j] = Pm[8 + j];
+      K[4 + j] = Pm[12 + j];
+      K[8 + j] = fx[0] * Pm[j] + fx[1] * Pm[4 + j] + fx[2] * Pm[8 + j] + fx[3] * Pm[12 + j];
+      K[12 + j] = fth[0] * Pm[j] + fth[1] * Pm[4 + j] + fth[2] * Pm[8 + j] + fth[3] * Pm[12 + j];
+    }
+    // ku = (F * ku_prev) * cprev + Fu
+    const double k0 = ku[2] * cprev, k1 = ku[3] * cprev;
+    const double k2 = (fx[0] * ku[0] + fx[1] * ku[1] + fx[2] * ku[2] + fx[3] * ku[3]) * cprev + gx;
+    const double k3 = (fth[0] * ku[0] + fth[1] * ku[1] + fth[2] * ku[2] + fth[3] * ku[3]) * cprev + gth;
+    ku[0] = k0;
+    ku[1] = k1;
+    ku[2] = k2;
+    ku[3] = k3;
+    const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) A[i] += K[i] * wgt;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) Bv[i] += ku[i] * wgt;
+    s0 += a2 * wgt;
+    s1 += a3 * wgt;
+    s2 += ax * wgt;
+    s3 += at * wgt;
+    const double cst = (st == 2) ? h : hh;
+    const double n0 = x[0] + a2 * cst, n1 = x[1] + a3 * cst, n2 = x[2] + ax * cst, n3 = x[3] + at * cst;
+    a0 = n0;
+    a1 = n1;
+    a2 = n2;
+    a3 = n3;
+    cprev = cst;
   }
-
-  // stage 4
-  const double v4x = x[2] + a3x * h, v4t = x[3] + a3t * h;
-  double a4x, a4t;
-  dyn_eval_jac(P, x[0] + v3x * h, x[1] + v3t * h, v4x, v4t, u, a4x, a4t, fx, fth, gx, gth);
-  stage_mul(fx, fth, Pm, K);
-  kun[0] = ku[2] * h;
-  kun[1] = ku[3] * h;
-  kun[2] = (fx[0] * ku[0] + fx[1] * ku[1] + fx[2] * ku[2] + fx[3] * ku[3]) * h + gx;
-  kun[3] = (fth[0] * ku[0] + fth[1] * ku[1] + fth[2] * ku[2] + fth[3] * ku[3]) * h + gth;
-
   const double h6 = h / 6.0;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) A[i] = ((i % 5 == 0) ? 1.0 : 0.0) + h6 * (A[i] + K[i]);
+  for (int i = 0; i < 16; ++i) A[i] = ((i % 5 == 0) ? 1.0 : 0.0) + h6 * A[i];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) Bv[i] = h6 * (Bv[i] + kun[i]);
-
-  const double n0 = x[0] + h6 * (x[2] + v2x * 2.0 + v3x * 2.0 + v4x);
-  const double n1 = x[1] + h6 * (x[3] + v2t * 2.0 + v3t * 2.0 + v4t);
-  const double n2 = x[2] + h6 * (a1x + a2x * 2.0 + a3x * 2.0 + a4x);
-  const double n3 = x[3] + h6 * (a1t + a2t * 2.0 + a3t * 2.0 + a4t);
-  x[0] = n0;
-  x[1] = n1;
-  x[2] = n2;
-  x[3] = n3;
+  for (int i = 0; i < 4; ++i) Bv[i] = h6 * Bv[i];
+  x[0] += h6 * s0;
+  x[1] += h6 * s1;
+  x[2] += h6 * s2;
+  x[3] += h6 * s3;
 }
 
 }  // namespace cpmpc

@@ -765,9 +765,9 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
 // ---------------------------------------------------------------------------------------------------------------------
 // Kernel: persistent grid-stride over instances; each warp carries 32/L instances at a time.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int L, int WARPS_PER_BLOCK>
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
-    cpmpc_solve_kernel(const KernelCfg cfg, const KernelIO io) {
+template <int L>
+__global__ void __launch_bounds__(128, 1) cpmpc_solve_kernel(const KernelCfg cfg, const KernelIO io) {
+  const int WARPS_PER_BLOCK = blockDim.x >> 5;  // 1, 2 or 4: one warp per SM sub-partition
   extern __shared__ double smem[];
   constexpr int G = 32 / L;
   const int lane = threadIdx.x & 31;

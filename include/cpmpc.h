@@ -118,6 +118,9 @@ int cpmpc_step_device(cpmpc_handle h, const double* states, const double* dyn_pa
 /* Replaces `Optimization::Reset()` (optimization.hpp:83).  mask: HOST [B] bytes, non-zero = reset; NULL = all. */
 int cpmpc_reset(cpmpc_handle h, const uint8_t* mask);
 
+/* Asynchronous Reset() of every instance, ordered on `stream` (a cudaStream_t; NULL = default stream). */
+int cpmpc_reset_device(cpmpc_handle h, void* stream);
+
 /* Replaces `Optimization::SetPreviousSolution` (optimization.hpp:86-89).  solutions: HOST [B*N].
  * mask: HOST [B] (non-zero = set), NULL = all. */
 int cpmpc_set_previous_solution(cpmpc_handle h, const double* solutions, const uint8_t* mask);
