@@ -13,7 +13,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libcpmpc.so")
 SOURCES = ["cpmpc_capi.cu"]
-HEADERS = ["solver_kernel.cuh", "dynamics.cuh", os.path.join("..", "..", "include", "cpmpc.h")]
+HEADERS = ["solver_kernel.cuh", "dynamics.cuh", "fastmath.cuh", os.path.join("..", "..", "include", "cpmpc.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

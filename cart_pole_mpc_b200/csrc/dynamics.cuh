@@ -11,9 +11,13 @@
 //   * the state Jacobian of the dynamics has two constant rows ([0 0 1 0], [0 0 0 1]); only rows 2-3 (8 numbers) and
 //     the two non-zero entries of the control Jacobian are produced, and the RK4 chain rule uses that structure
 //     (32 instead of 64 FMAs per stage product);
+//   * sin/cos, tanh, sqrt and the reciprocals come from fastmath.cuh (branch-free, ~1 ulp) so that one evaluation is
+//     a single basic block whose four long dependent chains overlap;
 //   * 1/(det*det) is computed as (1/det)^2 (1 ulp).
 #pragma once
 #include <cuda_runtime.h>
+
+#include "fastmath.cuh"
 
 namespace cpmpc {
 
@@ -70,28 +74,32 @@ template <bool FORCES>
 __device__ __forceinline__ void dyn_eval(const DynConst& P, const double b_x, const double th, const double b_xd,
                                          const double thd, const double u, const double fb_x, const double fm_x,
                                          const double fm_y, double& acc_x, double& acc_th) {
-  // one-sided bumper springs
+  // four independent chains start here: sincos(th), tanh(friction), bumper springs, and (after sin) 1/det
+  double s, c;
+  fm::sincos_bf(th, s, c);
+  const double fric = fm::tanh_bf(b_xd * P.inv_v_cut);
   const double over_r = b_x - P.x_s;
   const double pen_r = (0.0 < over_r) ? over_r : 0.0;
   const double over_l = -(b_x + P.x_s);
   const double pen_l = (0.0 < over_l) ? over_l : 0.0;
 
-  double s, c;
-  sincos(th, &s, &c);
+  const double s_m1 = s * P.m1;
+  const double det = P.m1 * (P.m_total - s_m1 * s);
+  const double inv_det = fm::rcp(det);
+
   const double lw = thd * P.len;
   const double cc = c * c;
   const double vx = b_xd - lw * s;
   const double lw_cc = lw * cc;
   const double speed_sq = lw * lw_cc + vx * vx;
-  const double speed15 = 1.5 * sqrt(speed_sq);
+  double speed, inv_speed;
+  fm::sqrt_rsqrt(speed_sq, speed, inv_speed);
+  const double speed15 = 1.5 * speed;
   const double proj = lw_cc - vx * s;
   const bool moving = 0.0 < speed_sq;
   const double drag_x = moving ? (vx * 2.0) * speed15 : 0.0;
   const double drag_th = moving ? proj * P.len2 * speed15 : 0.0;
 
-  const double s_m1 = s * P.m1;
-  const double fric = tanh(b_xd * P.inv_v_cut);
-  const double det = P.m1 * (P.m_total - s_m1 * s);
   double q_th, q_x;
   if (FORCES) {
     q_th = drag_th * P.drag_k + P.len * (c * (fm_y - P.grav * P.m1) - fm_x * s);
@@ -100,7 +108,6 @@ __device__ __forceinline__ void dyn_eval(const DynConst& P, const double b_x, co
     q_th = drag_th * P.drag_k + P.len * (c * (-(P.grav * P.m1)));
     q_x = u + fric * P.fric_k + drag_x * P.drag_k + P.m1 * lw * (thd * c) + P.k_s * (pen_l - pen_r);
   }
-  const double inv_det = 1.0 / det;
   const double num_th = q_x * (P.inv_len * s_m1) + q_th * P.m_over_l2;
   const double num_x = q_x + q_th * (s * P.inv_len);
   acc_x = num_x * (P.m1 * inv_det);
@@ -112,6 +119,9 @@ __device__ __forceinline__ void dyn_eval(const DynConst& P, const double b_x, co
 __device__ __forceinline__ void dyn_eval_jac(const DynConst& P, const double b_x, const double th, const double b_xd,
                                              const double thd, const double u, double& acc_x, double& acc_th,
                                              double fx[4], double fth[4], double& gx, double& gth) {
+  double s, c;
+  fm::sincos_bf(th, s, c);
+  const double fric = fm::tanh_bf(b_xd * P.inv_v_cut);
   const double over_r = b_x - P.x_s;
   const bool act_r = 0.0 < over_r;
   const double pen_r = act_r ? over_r : 0.0;
@@ -119,14 +129,17 @@ __device__ __forceinline__ void dyn_eval_jac(const DynConst& P, const double b_x
   const bool act_l = 0.0 < over_l;
   const double pen_l = act_l ? over_l : 0.0;
 
-  double s, c;
-  sincos(th, &s, &c);
+  const double s_m1 = s * P.m1;
+  const double det = P.m1 * (P.m_total - s_m1 * s);
+  const double inv_det = fm::rcp(det);
+
   const double lw = thd * P.len;
   const double cc = c * c;
   const double vx = b_xd - lw * s;
   const double lw_cc = lw * cc;
   const double speed_sq = lw * lw_cc + vx * vx;
-  const double speed = sqrt(speed_sq);
+  double speed, inv_speed;
+  fm::sqrt_rsqrt(speed_sq, speed, inv_speed);
   const double speed15 = 1.5 * speed;
   const double vx2 = vx * 2.0;
   const double proj = lw_cc - vx * s;
@@ -134,15 +147,11 @@ __device__ __forceinline__ void dyn_eval_jac(const DynConst& P, const double b_x
   const double drag_x = moving ? vx2 * speed15 : 0.0;
   const double drag_th = moving ? proj * P.len2 * speed15 : 0.0;
 
-  const double s_m1 = s * P.m1;
-  const double fric = tanh(b_xd * P.inv_v_cut);
-  const double det = P.m1 * (P.m_total - s_m1 * s);
   const double gm1 = P.grav * P.m1;
   const double q_th = drag_th * P.drag_k - P.len * (c * gm1);
   const double q_x = u + fric * P.fric_k + drag_x * P.drag_k + P.m1 * lw * (thd * c) + P.k_s * (pen_l - pen_r);
   const double s_m1_over_l = P.inv_len * s_m1;
   const double s_over_l = s * P.inv_len;
-  const double inv_det = 1.0 / det;
   const double inv_det_l = inv_det * P.inv_len;
   const double num_th = q_x * s_m1_over_l + q_th * P.m_over_l2;
   const double num_x = q_x + q_th * s_over_l;
@@ -151,19 +160,16 @@ __device__ __forceinline__ void dyn_eval_jac(const DynConst& P, const double b_x
   acc_x = num_x * gx;
   acc_th = inv_det * num_th;
 
-  // derivatives of the drag terms (zero at rest)
-  double d_th_q = 0.0, d_th_x = 0.0, d_v_l = 0.0, d_v_x = 0.0, d_w_th = 0.0;
-  if (moving) {
-    const double inv_speed = 1.0 / speed;
-    const double proj_n = 1.5 * (inv_speed * proj);
-    const double vx_rel = vx + s * lw;
-    const double speed3 = speed * 3.0;
-    d_th_q = -((lw * proj_n + speed15) * (c * P.len) * (2.0 * vx_rel));
-    d_th_x = -((inv_speed * vx_rel * (vx2 * 1.5) + speed3) * lw * c);
-    d_v_l = P.len * (vx2 * proj_n - speed3 * s);
-    d_v_x = vx2 * vx2 * (0.75 * inv_speed) + speed3;
-    d_w_th = P.len * (proj * proj_n + (cc + s * s) * speed15) * P.len2;
-  }
+  // derivatives of the drag terms (zero at rest): computed unconditionally, selected at the end
+  const double proj_n = 1.5 * (inv_speed * proj);
+  const double vx_rel = vx + s * lw;
+  const double speed3 = speed * 3.0;
+  const double d_th_q = moving ? -((lw * proj_n + speed15) * (c * P.len) * (2.0 * vx_rel)) : 0.0;
+  const double d_th_x = moving ? -((inv_speed * vx_rel * (vx2 * 1.5) + speed3) * lw * c) : 0.0;
+  const double d_v_l = moving ? P.len * (vx2 * proj_n - speed3 * s) : 0.0;
+  const double d_v_x = moving ? vx2 * vx2 * (0.75 * inv_speed) + speed3 : 0.0;
+  const double d_w_th = moving ? P.len * (proj * proj_n + (cc + s * s) * speed15) * P.len2 : 0.0;
+
   const double dq_th_dth = d_th_q * P.drag_k + P.len * (s * gm1);
   const double dq_x_dth = d_th_x * P.drag_k - lw * s_m1 * thd;
   const double m1_c = P.m1 * c;

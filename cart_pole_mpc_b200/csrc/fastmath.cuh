@@ -1,0 +1,162 @@
+// Branch-free FP64 elementary functions for the cart-pole dynamics on sm_100a.
+//
+// Why not libdevice: sin/cos/tanh/sqrt/1-over-x from the CUDA math library each carry a rarely-taken slow-path branch
+// (huge arguments, denormals).  Those branches split a dynamics evaluation into many basic blocks, and ptxas only
+// interleaves instructions inside a block — the four long dependent DFMA chains of one evaluation (sincos, tanh,
+// reciprocal of the mass-matrix determinant, sqrt of the tip speed) ended up strictly one after the other: 50 % of all
+// issue slots were `stall_wait` in the ncu profile of round 1 (profiles/r01_*).  The versions below are straight-line
+// code, accurate to about 1 ulp on the argument ranges this path can reach, so the scheduler can overlap the chains.
+//
+// Every function also compiles for the host (seed instructions replaced by float-precision seeds) so that
+// tests/test_fastmath.py can measure the ulp error without a GPU.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDA_ARCH__)
+#define CPMPC_HD __device__ __forceinline__
+#define CPMPC_FMA(a, b, c) fma((a), (b), (c))
+#else
+#ifdef __CUDACC__
+#define CPMPC_HD __host__ __device__ inline
+#else
+#define CPMPC_HD inline
+#endif
+#define CPMPC_FMA(a, b, c) fma((a), (b), (c))
+#endif
+
+namespace cpmpc {
+namespace fm {
+
+CPMPC_HD double rcp_seed(double x) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  return y;
+#else
+  return (double)(1.0f / (float)x);
+#endif
+}
+
+CPMPC_HD double rsqrt_seed(double x) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  return y;
+#else
+  return (double)(1.0f / sqrtf((float)x));
+#endif
+}
+
+// 1/x for normal, finite x (|x| in [1e-290, 1e290]); NaN/Inf propagate as NaN or 0.
+CPMPC_HD double rcp(double x) {
+  const double y0 = rcp_seed(x);
+  const double e = CPMPC_FMA(-x, y0, 1.0);
+  const double e2 = CPMPC_FMA(e, e, e);         // e + e^2
+  const double y1 = CPMPC_FMA(y0, e2, y0);      // y0 (1 + e + e^2): cubic step
+  const double e1 = CPMPC_FMA(-x, y1, 1.0);
+  return CPMPC_FMA(y1, e1, y1);
+}
+
+// sqrt(x) and 1/sqrt(x) for finite x > 0.  (x == 0 gives NaN: callers select it away.)
+CPMPC_HD void sqrt_rsqrt(double x, double& root, double& inv_root) {
+  const double y0 = rsqrt_seed(x);
+  double g = x * y0;     // ~ sqrt(x)
+  double h = 0.5 * y0;   // ~ 0.5 / sqrt(x)
+  double r = CPMPC_FMA(-g, h, 0.5);
+  g = CPMPC_FMA(g, r, g);
+  h = CPMPC_FMA(h, r, h);
+  r = CPMPC_FMA(-g, h, 0.5);
+  h = CPMPC_FMA(h, r, h);
+  const double d = CPMPC_FMA(-g, g, x);
+  root = CPMPC_FMA(d, h, g);
+  inv_root = h + h;
+}
+
+// sin and cos for |x| < 2^20 (the pole angle stays within a few turns between two mod_pi wraps).
+CPMPC_HD void sincos_bf(double x, double& s_out, double& c_out) {
+  // k = round(x * 2/pi) with the 1.5 * 2^52 trick; its low bits give the quadrant
+  const double magic = 6755399441055744.0;
+  const double t = CPMPC_FMA(x, 0.63661977236758138, magic);
+  const double kd = t - magic;
+  int64_t tb;
+#if defined(__CUDA_ARCH__)
+  tb = __double_as_longlong(t);
+#else
+  memcpy(&tb, &t, sizeof(tb));
+#endif
+  const int q = (int)(tb & 3);
+  // Cody-Waite with a three-part pi/2 (the FMAs keep the products exact)
+  double r = CPMPC_FMA(-kd, 1.5707963267948966, x);
+  r = CPMPC_FMA(-kd, 6.123233995736766e-17, r);
+  r = CPMPC_FMA(-kd, -1.4973849048591698e-33, r);
+  const double z = r * r;
+  // fdlibm kernel polynomials on |r| <= pi/4
+  double ps = CPMPC_FMA(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = CPMPC_FMA(z, ps, 2.75573137070700676789e-06);
+  ps = CPMPC_FMA(z, ps, -1.98412698298579493134e-04);
+  ps = CPMPC_FMA(z, ps, 8.33333333332248946124e-03);
+  ps = CPMPC_FMA(z, ps, -1.66666666666666324348e-01);
+  const double sn = CPMPC_FMA(z * r, ps, r);
+  double pc = CPMPC_FMA(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = CPMPC_FMA(z, pc, -2.75573143513906633035e-07);
+  pc = CPMPC_FMA(z, pc, 2.48015872894767294178e-05);
+  pc = CPMPC_FMA(z, pc, -1.38888888888741095749e-03);
+  pc = CPMPC_FMA(z, pc, 4.16666666666666019037e-02);
+  const double zz = z * z;
+  const double cs = CPMPC_FMA(zz, pc, CPMPC_FMA(-0.5, z, 1.0));
+  const bool swap = (q & 1) != 0;
+  const double sv = swap ? cs : sn;
+  const double cv = swap ? sn : cs;
+  s_out = (q & 2) ? -sv : sv;
+  c_out = ((q + 1) & 2) ? -cv : cv;
+}
+
+// tanh(x) with ABSOLUTE error ~2e-16 (enough here: it multiplies the friction force inside a sum of O(1) forces).
+CPMPC_HD double tanh_bf(double x) {
+  const double ax = fmin(fabs(x), 20.0);
+  const double y = -2.0 * ax;  // em = exp(y) in (4e-18, 1]
+  const double magic = 6755399441055744.0;
+  const double t = CPMPC_FMA(y, 1.4426950408889634, magic);
+  const double nd = t - magic;
+  int64_t tb;
+#if defined(__CUDA_ARCH__)
+  tb = __double_as_longlong(t);
+#else
+  memcpy(&tb, &t, sizeof(tb));
+#endif
+  const int n = (int)(int32_t)(tb & 0xffffffff);  // in [-58, 0]
+  double r = CPMPC_FMA(-nd, 6.93147180369123816490e-01, y);
+  r = CPMPC_FMA(-nd, 1.90821492927058770002e-10, r);
+  // exp(r), |r| <= ln2/2: Taylor to r^13, even/odd split to halve the dependent depth
+  const double r2 = r * r;
+  double pe = CPMPC_FMA(r2, 1.0 / 479001600.0, 1.0 / 3628800.0);  // r^12, r^10
+  pe = CPMPC_FMA(r2, pe, 1.0 / 40320.0);
+  pe = CPMPC_FMA(r2, pe, 1.0 / 720.0);
+  pe = CPMPC_FMA(r2, pe, 1.0 / 24.0);
+  pe = CPMPC_FMA(r2, pe, 0.5);
+  pe = CPMPC_FMA(r2, pe, 1.0);
+  double po = CPMPC_FMA(r2, 1.0 / 6227020800.0, 1.0 / 39916800.0);  // r^13, r^11
+  po = CPMPC_FMA(r2, po, 1.0 / 362880.0);
+  po = CPMPC_FMA(r2, po, 1.0 / 5040.0);
+  po = CPMPC_FMA(r2, po, 1.0 / 120.0);
+  po = CPMPC_FMA(r2, po, 1.0 / 6.0);
+  po = CPMPC_FMA(r2, po, 1.0);
+  const double er = CPMPC_FMA(r, po, pe);
+  // scale by 2^n (n in [-58, 0]: always a normal number)
+  const int64_t sb = (int64_t)(n + 1023) << 52;
+  double scale;
+#if defined(__CUDA_ARCH__)
+  scale = __longlong_as_double(sb);
+#else
+  memcpy(&scale, &sb, sizeof(scale));
+#endif
+  const double em = er * scale;
+  // tanh = (1 - em) / (1 + em)
+  const double th = (1.0 - em) * rcp(1.0 + em);
+  return copysign(th, x);
+}
+
+}  // namespace fm
+}  // namespace cpmpc
