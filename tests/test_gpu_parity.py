@@ -348,3 +348,13 @@ def test_fp64_peak_probe_is_plausible():
     from cart_pole_mpc_b200 import measure_fp64_peak
     t = measure_fp64_peak(0)
     assert 10.0 < t < 60.0, t   # B200 FP64 FMA pipe: ~37-40 TFLOP/s nominal
+
+
+def test_cpp_facade_runs_the_reference_closed_loop_test(tmp_path):
+    """optimization_test.cc:12-77 compiled against host/optimization.hpp (the C++ drop-in) and run on the GPU."""
+    import subprocess
+    from test_host_logic import _build_facade_test
+    exe = _build_facade_test(tmp_path)
+    proc = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout + proc.stderr
+    assert "FACADE_CLOSED_LOOP_OK" in proc.stdout

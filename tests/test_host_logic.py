@@ -175,3 +175,23 @@ def test_reference_arm_of_bench_prints_contract_line(oracle):
     assert line["impl"] == "reference" and line["unit"] == "solves/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
+
+
+def _build_facade_test(tmp_path):
+    from cart_pole_mpc_b200 import _capi
+    exe = tmp_path / "facade_closed_loop"
+    pkg = os.path.dirname(_capi.LIB_PATH)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-o", str(exe),
+                    os.path.join(ROOT, "tests", "native", "facade_closed_loop.cc"), "-L" + pkg, "-lcpmpc",
+                    "-Wl,-rpath," + pkg], check=True)
+    return exe
+
+
+def test_cpp_facade_compiles_against_the_c_abi(cuda_lib, tmp_path):
+    """The reference-shaped C++ API (host/optimization.hpp) builds with -Wall -Wextra -Werror and links to
+    libcpmpc.so; without a GPU the program must stop with the library's CUDA error, not compute anything."""
+    import torch
+    exe = _build_facade_test(tmp_path)
+    if not torch.cuda.is_available():
+        proc = subprocess.run([str(exe)], capture_output=True, text=True)
+        assert proc.returncode != 0 and "FACADE_CLOSED_LOOP_OK" not in proc.stdout
