@@ -55,7 +55,7 @@ struct cpmpc_solver {
   double* d_prev = nullptr;
   unsigned char* d_has_prev = nullptr;
   double* d_u_guess = nullptr;
-  double* d_lm = nullptr;
+  double* d_kk = nullptr;
   double* d_iter_log = nullptr;
   bool log_enabled = false;
   // staging for the host-buffer entry points
@@ -86,7 +86,7 @@ KernelFn SelectKernel(int lanes) {
   }
 }
 
-// Shared-memory layout of one instance (doubles).
+// Shared-memory layout of one instance (doubles).  `k.cps` must be set.
 void BuildLayout(KernelCfg& k) {
   int off = 0;
   auto take = [&off](int n) {
@@ -94,32 +94,32 @@ void BuildLayout(KernelCfg& k) {
     off += n;
     return o;
   };
-  const int W = k.W, NS = k.NS, nseg = k.nseg;
+  const int W = k.W, S = k.S, NS = k.NS, nseg = k.nseg;
+  k.nchunk = nseg * k.cps;
+  const int n_xk = (k.cps > 1) ? 4 * k.nchunk : 0;
   k.off_xs = take(4 * NS);
   k.off_u = take(W);
   k.off_dxs = take(4 * NS);
   k.off_du = take(W);
   k.off_phi = take(16 * nseg);
   k.off_e = take(4 * nseg);
-  k.off_gam = take(4 * W);
-  k.off_gdu = take(4 * nseg);
-  k.off_M = take(4 * W);
-  // the line-search candidates are only live after the QP has been solved: they alias the QP's U rows
-  k.off_xc = k.off_M;
-  k.off_uc = k.off_M + 4 * NS;
-  if (4 * NS + W > 4 * W) take(4 * NS + W - 4 * W);
-  k.off_Y = take(5 * W);
-  k.off_tl = take(W);
-  k.off_tinv = take(W);
-  k.off_gram = take(20);
-  k.off_sig = take(4);
-  k.off_inv_d = take(4);
-  k.off_moff = take(4);
+  k.off_xk = take(n_xk);
+  k.off_phic = take((k.cps > 1) ? 16 * k.nchunk : 0);
+  // the line-search candidates (shooting states, controls, chunk-start states) are only live after the QP has
+  // been solved: they alias the Gamma block
+  const int n_cand = 4 * NS + W + n_xk;
+  k.off_gam = take(4 * W > n_cand ? 4 * W : n_cand);
+  k.off_xc = k.off_gam;
+  k.off_uc = k.off_xc + 4 * NS;
+  k.off_xkc = k.off_uc + W;
+  // Riccati stage matrix over (S controls | xi | rho), packed lower triangle
+  const int D = S + NCOL_MAX;
+  k.off_aug = take(D * (D + 1) / 2);
+  k.off_vbuf = take(25 + XI_DIM * NR_MAX);
+  k.off_invd = take(S);
   // odd stride (in doubles) so that the same field of neighbouring instances falls into different banks
   k.stride = off | 1;
-  const int R = 4 * nseg;
-  k.lm_rows = R;
-  k.lm_stride = R * W + (R + 1) * W + R * (R + 1) + 3 * R;
+  k.kk_stride = nseg * NCOL_MAX * S;
 }
 
 int Launch(cpmpc_solver* h, KernelIO io, cudaStream_t stream) {
@@ -128,7 +128,7 @@ int Launch(cpmpc_solver* h, KernelIO io, cudaStream_t stream) {
   io.u_guess = h->d_u_guess;
   io.prev = h->d_prev;
   io.has_prev = h->d_has_prev;
-  io.lm_scratch = h->d_lm;
+  io.kk_scratch = h->d_kk;
   io.iter_log = h->log_enabled ? h->d_iter_log : nullptr;
   fn<<<h->grid, 32 * h->warps_per_block, h->smem_bytes, stream>>>(h->cfg, io);
   g_launches.fetch_add(1);
@@ -244,16 +244,26 @@ int cpmpc_create(const cpmpc_params* params, int64_t batch, int device, cpmpc_ha
   k.wt[3] = params->th_dot_final_cost_weight;
   k.x_clamp = 5.0;    // optimization.cc:320
   k.u_clamp = 300.0;  // optimization.cc:327
-  BuildLayout(k);
-
-  // lanes per instance: one lane per shooting segment (power of two), overridable for experiments
-  int lanes = Pow2Ceil(k.nseg);
-  if (lanes > 32) lanes = 32;
+  // Lanes per instance.  One lane per shooting segment is the minimum that keeps the merit rollouts parallel; twice
+  // that (when a segment has at least two knots) lets the linearisation run two chunks per segment side by side and
+  // halves its dependent chain.  Overridable for experiments.
+  int base_lanes = Pow2Ceil(k.nseg);
+  if (base_lanes > 32) base_lanes = 32;
+  int lanes = base_lanes;
+  if (2 * base_lanes <= 32 && k.S >= 2 && (2 * base_lanes) / k.nseg >= 2) lanes = 2 * base_lanes;
   if (const char* env = std::getenv("CPMPC_LANES")) {
     const int v = std::atoi(env);
     if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) lanes = v;
   }
   h->lanes = lanes;
+  k.cps = lanes / k.nseg;
+  if (k.cps < 1) k.cps = 1;
+  if (k.cps > k.S) k.cps = k.S;
+  if (const char* env = std::getenv("CPMPC_CHUNKS")) {
+    const int v = std::atoi(env);
+    if (v >= 1 && v <= k.S && v * k.nseg <= lanes) k.cps = v;
+  }
+  BuildLayout(k);
   const int groups_per_warp = 32 / lanes;
   const size_t smem_per_warp = sizeof(double) * static_cast<size_t>(k.stride) * groups_per_warp;
 
@@ -265,14 +275,20 @@ int cpmpc_create(const cpmpc_params* params, int64_t batch, int device, cpmpc_ha
                                            " bytes of shared memory per warp, device offers " +
                                            std::to_string(prop.sharedMemPerBlockOptin));
   }
-  // Up to 4 warps per block so that the warps of one block sit on the 4 sub-partitions of an SM (a block of ONE warp
-  // lets several blocks pile onto the same sub-partition and serialise on its FP64 pipe).
-  int wpb = 4;
+  // One block per SM, up to 8 warps (two per SM sub-partition; 8 x 32 x 255 registers fill the register file).  A
+  // batch that needs fewer warps than that is spread evenly over the SMs instead of filling some and idling others.
+  int wpb_max = 8;
   if (const char* env = std::getenv("CPMPC_WARPS_PER_BLOCK")) {
     const int v = std::atoi(env);
-    if (v == 1 || v == 2 || v == 4) wpb = v;
+    if (v >= 1 && v <= 8) wpb_max = v;
   }
-  while (wpb > 1 && smem_per_warp * wpb > static_cast<size_t>(prop.sharedMemPerBlockOptin)) wpb >>= 1;
+  while (wpb_max > 1 && smem_per_warp * wpb_max > static_cast<size_t>(prop.sharedMemPerBlockOptin)) --wpb_max;
+  const long long warps_needed = (batch + groups_per_warp - 1) / groups_per_warp;
+  int wpb = wpb_max;
+  if (warps_needed <= static_cast<long long>(wpb_max) * prop.multiProcessorCount) {
+    wpb = static_cast<int>((warps_needed + prop.multiProcessorCount - 1) / prop.multiProcessorCount);
+    if (wpb < 1) wpb = 1;
+  }
   h->warps_per_block = wpb;
   h->smem_bytes = smem_per_warp * wpb;
   KernelFn fn = SelectKernel(lanes);
@@ -293,7 +309,7 @@ int cpmpc_create(const cpmpc_params* params, int64_t batch, int device, cpmpc_ha
   CUDA_TRY(cudaMalloc(&h->d_has_prev, batch));
   CUDA_TRY(cudaMemset(h->d_has_prev, 0, batch));
   CUDA_TRY(cudaMemset(h->d_prev, 0, sizeof(double) * batch * k.N));
-  CUDA_TRY(cudaMalloc(&h->d_lm, sizeof(double) * n_groups * k.lm_stride));
+  CUDA_TRY(cudaMalloc(&h->d_kk, sizeof(double) * n_groups * k.kk_stride));
   CUDA_TRY(cudaMalloc(&h->d_u_guess, sizeof(double) * k.W));
   // cold-start sinusoid with the host's libm, exactly as optimization.cc:63-67 evaluates it
   std::vector<double> guess(k.W);
@@ -313,7 +329,7 @@ int cpmpc_destroy(cpmpc_handle h) {
   cudaFree(h->d_prev);
   cudaFree(h->d_has_prev);
   cudaFree(h->d_u_guess);
-  cudaFree(h->d_lm);
+  cudaFree(h->d_kk);
   cudaFree(h->d_iter_log);
   cudaFree(h->d_states);
   cudaFree(h->d_dyn);

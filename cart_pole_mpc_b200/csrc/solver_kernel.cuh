@@ -4,20 +4,26 @@
 // (optimization/optimization.cc:39-97 -> mini_opt nonlinear.cc:75-158), re-organised around the structure of THIS
 // problem instead of a generic dense QP:
 //
-//   * lane s of a group owns shooting segment s: it rolls the dynamics out through S RK4 steps in registers
-//     (with the Jacobian chain in forward mode when linearising) — rows a1-a3 of SURVEY.md section 8a;
+//   * linearisation (rows a1-a3 of SURVEY.md section 8a): every shooting segment is cut into `cps` chunks of
+//     consecutive knots; one lane integrates one chunk through RK4 with the Jacobian chain folded in forward mode,
+//     starting from the chunk-start state that the last accepted merit rollout left behind, and the chunk blocks are
+//     then multiplied together.  The dependent chain of a linearisation is S/cps RK4 steps instead of S;
 //   * the equality-constrained QP (reference: dense column-pivoted QR + explicit Q + 37x37 Cholesky, qp.cc:679-729)
-//     is solved in condensed form.  With the shooting states eliminated forward through the linearised dynamics the
-//     Hessian over the W controls is  T + U^T D U : T is the tridiagonal control/control-rate Hessian (+ lambda),
-//     and U holds only the rows of the state sensitivities that carry a cost or a hard terminal constraint
-//     (4 rows when lambda = 0, 4*(NS-1) rows in Levenberg-Marquardt mode).  T is factored in O(W), the rows are
-//     handled through an (R x R) Schur complement.  The step dx is identical to the reference's null-space solution
-//     (the QP is strictly convex on the constraint null space, so the solution is unique);
+//     is solved by a segment-wise Riccati recursion.  Stage = one shooting segment, stage state xi = (node step dx_s,
+//     previous control), stage control = the S knots of the segment.  Per stage a symmetric matrix over
+//     (controls | xi | rho) is assembled in shared memory (rho = the affine coordinate plus one multiplier coordinate
+//     per hard terminal row) and S steps of right-looking Cholesky eliminate the controls: the trailing block IS the
+//     next value function, the sub-diagonal panel gives the feedback gains.  The multipliers of the hard terminal
+//     rows come from a (<= 4x4) Cholesky on the rho block, one forward sweep yields du and the node steps.
+//     Levenberg-Marquardt damping (lambda on every diagonal entry of G, nonlinear.cc:187-189) is just a stage cost.
+//     The step is the reference's null-space solution (the QP is strictly convex on the constraint null space);
+//     closed-loop propagation keeps it accurate for long, unstable horizons where open-loop condensing is not
+//     (tests/prototypes/qp_riccati_proto.py);
 //   * the L1-merit polynomial line search, penalty update, LM state machine and exit tests follow
 //     nonlinear.cc:296-605 branch for branch, run in lock step by the groups of a warp.
 //
-// All per-instance state lives in shared memory (about 7 KB at W=40,S=10); HBM is touched only for the inputs,
-// the warm start and the results.
+// All per-instance state lives in shared memory (about 5.5 KB at W=40,S=10) except the Riccati gains, which go
+// through an L2-resident global scratch; HBM is touched only for the inputs, the warm start and the results.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,13 +33,18 @@
 
 namespace cpmpc {
 
+constexpr int NR_MAX = 5;              // rho coordinates: affine + up to 4 hard terminal rows
+constexpr int XI_DIM = 5;              // stage state: node step (4) + previous control (1)
+constexpr int NCOL_MAX = XI_DIM + NR_MAX;
+
 struct KernelCfg {
   int W, S, NS, nseg, N, max_iter, max_ls;
+  int cps;     // chunks per shooting segment in the linearisation
+  int nchunk;  // nseg * cps
   int stride;  // doubles of shared memory per instance
-  int off_xs, off_u, off_xc, off_uc, off_dxs, off_du, off_phi, off_e, off_gam, off_gdu, off_M, off_Y, off_tl,
-      off_tinv, off_gram, off_sig, off_inv_d, off_moff;
-  int lm_rows;    // 4 * (NS - 1)
-  int lm_stride;  // doubles of global scratch per group for the Levenberg-Marquardt path
+  int off_xs, off_u, off_dxs, off_du, off_phi, off_e, off_gam, off_xk, off_phic, off_aug, off_vbuf, off_invd;
+  int off_xc, off_uc, off_xkc;  // line-search candidates: alias the Gamma block (dead after the QP)
+  int kk_stride;                // doubles of global scratch per group: nseg * NCOL_MAX * S Riccati gains
   double dt, rel_tol, first_tol, abs_tol, pen_init, pen_scale, rho, armijo_c1;
   double lam_fail_init, lam_dec_success, lam_dec_restore, lam_max, lam_min;
   double w_u, w_r, wt[4];
@@ -53,7 +64,7 @@ struct KernelIO {
   double* pred_out;          // [B,W,4] or nullptr
   cpmpc_stats* stats;        // [B] or nullptr
   double* iter_log;          // [B,max_iter,27] or nullptr
-  double* lm_scratch;        // [n_groups, lm_stride]
+  double* kk_scratch;        // [n_groups, kk_stride]
   // closed loop (n_sim_steps > 0): the plant state is integrated forward with u[0] after every solve
   long long n_steps;         // number of Step()+Simulator::Step() rounds (1 and no plant update when sim == 0)
   int sim;                   // 1 = closed loop
@@ -88,7 +99,7 @@ struct Weights {
 struct Ctx {
   const KernelCfg* cfg;
   double* sm;  // this instance's shared memory
-  double* lm;  // this group's global LM scratch
+  double* kk;  // this group's global scratch for the Riccati gains
   int gl;      // lane within the group
   unsigned gmask;
 };
@@ -160,16 +171,32 @@ __device__ __forceinline__ void boundary_terms(const KernelCfg& k, const Weights
 // ---------------------------------------------------------------------------------------------------------------------
 // One merit evaluation == EvaluateNonlinearErrors (nonlinear.cc:279-293) on the shooting states `xx` / controls `uu`.
 // Each lane integrates its own segments without Jacobians; the defects against the next shooting state are L1-summed.
+// The states at the chunk boundaries inside a segment are left in `xk_out` for the next linearisation.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int L>
 __device__ __forceinline__ void evaluate_errors(const Ctx& c, const DynConst& P, const Weights& w, const double* xx,
-                                                const double* uu, const double x_cur[4], const double set_point,
-                                                const double u_prev, double& f_out, double& eq_out) {
+                                                const double* uu, double* xk_out, const double x_cur[4],
+                                                const double set_point, const double u_prev, double& f_out,
+                                                double& eq_out) {
   const KernelCfg& k = *c.cfg;
+  const int S = k.S, cps = k.cps;
   double eq = 0.0;
   for (int s = c.gl; s < k.nseg; s += L) {
     double x[4] = {xx[4 * s], xx[4 * s + 1], xx[4 * s + 2], xx[4 * s + 3]};
-    for (int i = 0; i < k.S; ++i) rk4_step<false>(P, x, uu[s * k.S + i], k.dt);
+    int cc = 1;
+    int nb = (cps > 1) ? (S / cps) : S;  // first step of chunk cc
+    for (int i = 0; i < S; ++i) {
+      if (i == nb) {
+        double* dst = xk_out + 4 * (s * cps + cc);
+        dst[0] = x[0];
+        dst[1] = x[1];
+        dst[2] = x[2];
+        dst[3] = x[3];
+        ++cc;
+        nb = (cc < cps) ? (cc * S) / cps : S;
+      }
+      rk4_step<false>(P, x, uu[s * S + i], k.dt);
+    }
     x[1] = mod_pi(x[1]);
     const double* xn = xx + 4 * (s + 1);
     eq += fabs(x[0] - xn[0]);
@@ -188,35 +215,303 @@ __device__ __forceinline__ void evaluate_errors(const Ctx& c, const DynConst& P,
   eq_out = group_sum<L>(eq, c.gmask);
 }
 
-// Tridiagonal LDL^T of T = diag(a_k) + offdiag(-w_r^2): a_k = w_u^2 + lambda + w_r^2 * n_k where n_k counts the
-// control-rate residuals touching u_k (2, or 1 for the last knot).  One lane; returns false on a non-positive pivot.
-__device__ __forceinline__ bool factor_tridiagonal(const KernelCfg& k, const Weights& w, const double lambda,
-                                                   double* tl, double* tinv) {
-  const double wu2 = w.w_u * w.w_u, wr2 = w.w_r * w.w_r;
-  const double off = -wr2;
-  double d_prev = 0.0;
-  bool ok = true;
-  for (int j = 0; j < k.W; ++j) {
-    const double a = wu2 + lambda + wr2 * ((j + 1 < k.W) ? 2.0 : 1.0);
-    double l = 0.0, d = a;
-    if (j > 0) {
-      l = off * tinv[j - 1];
-      d = a - l * off;
-    }
-    ok = ok && (d > 0.0);
-    tl[j] = l;
-    tinv[j] = 1.0 / d;
-    d_prev = d;
-  }
-  (void)d_prev;
-  return ok;
-}
+// Packed lower-triangular index.
+__device__ __forceinline__ int tri(const int r, const int col) { return ((r * (r + 1)) >> 1) + col; }
 
-// In-place solve T y = r with the factorisation above (r has stride 1, length W).
-__device__ __forceinline__ void solve_tridiagonal(const int W, const double* tl, const double* tinv, double* r) {
-  for (int j = 1; j < W; ++j) r[j] -= tl[j] * r[j - 1];
-  r[W - 1] *= tinv[W - 1];
-  for (int j = W - 2; j >= 0; --j) r[j] = r[j] * tinv[j] - tl[j + 1] * r[j + 1];
+// ---------------------------------------------------------------------------------------------------------------------
+// Equality-constrained QP of one SQP iteration (reference: QPNullSpaceSolver::Solve, qp.cc:679-729) by a segment-wise
+// Riccati recursion; see the header comment.  On entry Phi / Gam / ev hold the segment blocks, du[] the gradient of
+// the control costs.  On exit du[] and dxs[] hold the step; returns false when a pivot is not positive (the reduced
+// Hessian is not positive definite: QP_INDEFINITE).  `cdx` returns this lane's share of c_u . du.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int L>
+__device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights& w, const double lambda,
+                                           const double x_cur[4], const double target[4], double& cdx) {
+  const KernelCfg& k = *c.cfg;
+  const int W = k.W, S = k.S, NS = k.NS, nseg = k.nseg;
+  const double* xs = c.sm + k.off_xs;
+  double* dxs = c.sm + k.off_dxs;
+  double* du = c.sm + k.off_du;
+  const double* Phi = c.sm + k.off_phi;
+  const double* ev = c.sm + k.off_e;
+  const double* Gam = c.sm + k.off_gam;
+  double* aug = c.sm + k.off_aug;
+  double* vb = c.sm + k.off_vbuf;  // [25] P (full, symmetric) then [5][NR_MAX] q
+  double* qb = vb + 25;
+  double* invd = c.sm + k.off_invd;
+  const double wu2 = w.w_u * w.w_u, wr2 = w.w_r * w.w_r;
+
+  // hard terminal rows (negative weight, optimization.cc:236-267) and their rho coordinates
+  int nh = 0;
+  int hcomp[4] = {0, 0, 0, 0};  // state component of hard row j
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (w.wt[i] < 0.0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j == nh) hcomp[j] = i;
+      ++nh;
+    }
+  }
+  const int nr = 1 + nh;
+  const int n2 = XI_DIM + nr;
+  const int D = S + n2;
+  double dT[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double d = xs[4 * (NS - 1) + i] - target[i];
+    if (i == 1) d = mod_pi(d);
+    dT[i] = d;
+  }
+
+  // terminal value function V_N over (xi | rho), stored where a stage elimination leaves it: rows/cols S..D-1
+  for (int a = c.gl; a < n2; a += L) {
+    for (int b = 0; b <= a; ++b) {
+      double v = 0.0;
+      if (a < 4) {
+        if (a == b) {
+          const double wa = (a == 0) ? w.wt[0] : (a == 1) ? w.wt[1] : (a == 2) ? w.wt[2] : w.wt[3];
+          v = lambda + ((wa >= 0.0) ? wa * wa : 0.0);
+        }
+      } else if (a == XI_DIM && b < 4) {
+        const double wb = (b == 0) ? w.wt[0] : (b == 1) ? w.wt[1] : (b == 2) ? w.wt[2] : w.wt[3];
+        const double db = (b == 0) ? dT[0] : (b == 1) ? dT[1] : (b == 2) ? dT[2] : dT[3];
+        v = (wb >= 0.0) ? (wb * wb) * db : 0.0;
+      } else if (a > XI_DIM && b < 4) {
+        const int j = a - XI_DIM - 1;
+        const int hj = (j == 0) ? hcomp[0] : (j == 1) ? hcomp[1] : (j == 2) ? hcomp[2] : hcomp[3];
+        v = (b == hj) ? 1.0 : 0.0;
+      }
+      aug[tri(S + a, S + b)] = v;
+    }
+  }
+  CPMPC_GSYNC();
+
+  bool ok = true;
+  for (int s = nseg - 1; s >= 0 && ok; --s) {
+    const double* Ph = Phi + 16 * s;
+    const double f0 = ev[4 * s], f1 = ev[4 * s + 1], f2 = ev[4 * s + 2], f3 = ev[4 * s + 3];
+    // (i) snapshot P (full 5x5) and q = p + (P f) e_0; fold f . p_r into the rho-rho column 0 (in place)
+    for (int t = c.gl; t < 25 + XI_DIM * nr + nh; t += L) {
+      if (t < 25) {
+        const int a = t / 5, b = t - 5 * a;
+        vb[t] = (a >= b) ? aug[tri(S + a, S + b)] : aug[tri(S + b, S + a)];
+      } else if (t < 25 + XI_DIM * nr) {
+        const int t2 = t - 25;
+        const int r = t2 / XI_DIM, a = t2 - XI_DIM * r;
+        double v = aug[tri(S + XI_DIM + r, S + a)];
+        if (r == 0) {
+          const double p0 = (a >= 0) ? aug[tri(S + a, S + 0)] : 0.0;
+          const double p1 = (a >= 1) ? aug[tri(S + a, S + 1)] : aug[tri(S + 1, S + a)];
+          const double p2 = (a >= 2) ? aug[tri(S + a, S + 2)] : aug[tri(S + 2, S + a)];
+          const double p3 = (a >= 3) ? aug[tri(S + a, S + 3)] : aug[tri(S + 3, S + a)];
+          v += p0 * f0 + p1 * f1 + p2 * f2 + p3 * f3;
+        }
+        qb[a * NR_MAX + r] = v;
+      } else {
+        const int r = t - 25 - XI_DIM * nr + 1;  // 1..nh
+        const double* pr = aug + tri(S + XI_DIM + r, S);
+        aug[tri(S + XI_DIM + r, S + XI_DIM)] += pr[0] * f0 + pr[1] * f1 + pr[2] * f2 + pr[3] * f3;
+      }
+    }
+    CPMPC_GSYNC();
+
+    // (ii) assemble the stage matrix, one column per lane
+    for (int t = c.gl; t < S + XI_DIM; t += L) {
+      if (t < S) {
+        const int j = t, col = s * S + j;
+        const double g0 = Gam[col], g1 = Gam[W + col], g2 = Gam[2 * W + col], g3 = Gam[3 * W + col];
+        const double g4 = (j == S - 1) ? 1.0 : 0.0;
+        double PG[XI_DIM];
+#pragma unroll
+        for (int a = 0; a < XI_DIM; ++a)
+          PG[a] = vb[5 * a] * g0 + vb[5 * a + 1] * g1 + vb[5 * a + 2] * g2 + vb[5 * a + 3] * g3 + vb[5 * a + 4] * g4;
+        for (int i = j; i < S; ++i) {
+          const int ci = s * S + i;
+          double v = Gam[ci] * PG[0] + Gam[W + ci] * PG[1] + Gam[2 * W + ci] * PG[2] + Gam[3 * W + ci] * PG[3];
+          if (i == S - 1) v += PG[4];
+          if (i == j) v += wu2 + lambda + wr2 * ((col + 1 < W) ? 2.0 : 1.0);
+          if (i == j + 1) v -= wr2;
+          aug[tri(i, j)] = v;
+        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+          aug[tri(S + cc, j)] = Ph[cc] * PG[0] + Ph[4 + cc] * PG[1] + Ph[8 + cc] * PG[2] + Ph[12 + cc] * PG[3];
+        aug[tri(S + 4, j)] = (j == 0 && s > 0) ? -wr2 : 0.0;
+        for (int r = 0; r < nr; ++r) {
+          double v = g0 * qb[r] + g1 * qb[NR_MAX + r] + g2 * qb[2 * NR_MAX + r] + g3 * qb[3 * NR_MAX + r] +
+                     g4 * qb[4 * NR_MAX + r];
+          if (r == 0) v += du[col];
+          aug[tri(S + XI_DIM + r, j)] = v;
+        }
+      } else {
+        const int cc = t - S;  // xi column
+        if (cc < 4) {
+          const double h0 = Ph[cc], h1 = Ph[4 + cc], h2 = Ph[8 + cc], h3 = Ph[12 + cc];
+          double PF[4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) PF[a] = vb[5 * a] * h0 + vb[5 * a + 1] * h1 + vb[5 * a + 2] * h2 + vb[5 * a + 3] * h3;
+          for (int c2 = cc; c2 < 4; ++c2) {
+            double v = Ph[c2] * PF[0] + Ph[4 + c2] * PF[1] + Ph[8 + c2] * PF[2] + Ph[12 + c2] * PF[3];
+            if (c2 == cc && s > 0) v += lambda;
+            aug[tri(S + c2, S + cc)] = v;
+          }
+          aug[tri(S + 4, S + cc)] = 0.0;
+          for (int r = 0; r < nr; ++r)
+            aug[tri(S + XI_DIM + r, S + cc)] =
+                h0 * qb[r] + h1 * qb[NR_MAX + r] + h2 * qb[2 * NR_MAX + r] + h3 * qb[3 * NR_MAX + r];
+        } else {
+          aug[tri(S + 4, S + 4)] = 0.0;
+          for (int r = 0; r < nr; ++r) aug[tri(S + XI_DIM + r, S + 4)] = 0.0;
+        }
+      }
+    }
+    CPMPC_GSYNC();
+
+    // (iii) eliminate the S controls: right-looking Cholesky steps over the whole D x D matrix
+    for (int j = 0; j < S; ++j) {
+      const double piv = aug[tri(j, j)];
+      if (!(piv > 0.0)) {
+        ok = false;
+        break;
+      }
+      double root, inv;
+      fm::sqrt_rsqrt(piv, root, inv);
+      if (c.gl == 0) invd[j] = inv;
+      for (int r = j + 1 + c.gl; r < D; r += L) aug[tri(r, j)] *= inv;
+      CPMPC_GSYNC();
+      for (int r = j + 1 + c.gl; r < D; r += L) {
+        double* row = aug + tri(r, 0);
+        const double lrj = row[j];
+        for (int cc = j + 1; cc <= r; ++cc) row[cc] -= lrj * aug[tri(cc, j)];
+      }
+      CPMPC_GSYNC();
+    }
+    if (!ok) break;
+
+    // (iv) gains: rows S.. of the panel hold (L^-1 B)^T; back-substitute to (H_vv^-1 B)^T in place, then spill
+    for (int q = c.gl; q < n2; q += L) {
+      double* row = aug + tri(S + q, 0);
+      for (int j = S - 1; j >= 0; --j) {
+        const double xj = row[j] * invd[j];
+        row[j] = xj;
+        const double* Lj = aug + tri(j, 0);
+        for (int i = 0; i < j; ++i) row[i] -= Lj[i] * xj;
+      }
+      double* dst = c.kk + ((size_t)s * NCOL_MAX + q) * S;
+      for (int j = 0; j < S; ++j) __stcg(dst + j, row[j]);
+    }
+    CPMPC_GSYNC();
+  }
+  ok = __all_sync(c.gmask, ok);
+  if (!ok) return false;
+
+  // multipliers of the hard terminal rows: x_N[h_j](mu) + d_j = 0 with x_N[h_j] = p_j . xi_0 + C_j0 + sum_k C_jk mu_k
+  double m0[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double d = xs[i] - x_cur[i];
+    if (i == 1) d = mod_pi(d);
+    m0[i] = -d;
+  }
+  double coef[NR_MAX] = {1.0, 0.0, 0.0, 0.0, 0.0};
+  if (nh > 0) {
+    double Mh[4][4], rhs[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      rhs[j] = 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) Mh[j][q] = (j == q) ? 1.0 : 0.0;
+      if (j < nh) {
+        const double* pr = aug + tri(S + XI_DIM + 1 + j, S);
+        const int hj = hcomp[j];
+        const double dj = (hj == 0) ? dT[0] : (hj == 1) ? dT[1] : (hj == 2) ? dT[2] : dT[3];
+        rhs[j] = pr[0] * m0[0] + pr[1] * m0[1] + pr[2] * m0[2] + pr[3] * m0[3] + pr[XI_DIM] + dj;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q <= j) Mh[j][q] = -pr[XI_DIM + 1 + q];
+      }
+    }
+    // Cholesky of the (nh x nh) lower triangle, rows >= nh are identity
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double d = Mh[j][j];
+#pragma unroll
+      for (int q = 0; q < j; ++q) d -= Mh[j][q] * Mh[j][q];
+      if (!(d > 0.0)) ok = false;
+      const double inv = 1.0 / sqrt(d);
+      Mh[j][j] = inv;  // keep the reciprocal
+#pragma unroll
+      for (int i = j + 1; i < 4; ++i) {
+        double sacc = Mh[i][j];
+#pragma unroll
+        for (int q = 0; q < j; ++q) sacc -= Mh[i][q] * Mh[j][q];
+        Mh[i][j] = sacc * inv;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double sacc = rhs[i];
+#pragma unroll
+      for (int q = 0; q < i; ++q) sacc -= Mh[i][q] * rhs[q];
+      rhs[i] = sacc * Mh[i][i];
+    }
+#pragma unroll
+    for (int i = 3; i >= 0; --i) {
+      double sacc = rhs[i];
+#pragma unroll
+      for (int q = i + 1; q < 4; ++q) sacc -= Mh[q][i] * rhs[q];
+      rhs[i] = sacc * Mh[i][i];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) coef[1 + j] = (j < nh) ? rhs[j] : 0.0;
+    if (!ok) return false;
+  }
+
+  // forward sweep: v = -(K xi + k . coef), xi+ = Phi xi + Gam v + e
+  double xi[XI_DIM] = {m0[0], m0[1], m0[2], m0[3], 0.0};
+  if (c.gl == 0) {
+    dxs[0] = m0[0];
+    dxs[1] = m0[1];
+    dxs[2] = m0[2];
+    dxs[3] = m0[3];
+  }
+  cdx = 0.0;
+  for (int s = 0; s < nseg; ++s) {
+    const double* kks = c.kk + (size_t)s * NCOL_MAX * S;
+    for (int j = c.gl; j < S; j += L) {
+      double acc = 0.0;
+#pragma unroll
+      for (int q = 0; q < XI_DIM; ++q) acc += __ldcg(kks + q * S + j) * xi[q];
+#pragma unroll
+      for (int r = 0; r < NR_MAX; ++r)
+        if (r < nr) acc += __ldcg(kks + (XI_DIM + r) * S + j) * coef[r];
+      const int col = s * S + j;
+      const double v = -acc;
+      cdx += du[col] * v;  // du[] still holds c_u
+      du[col] = v;
+    }
+    CPMPC_GSYNC();
+    const double* Ph = Phi + 16 * s;
+    for (int a = c.gl; a < 4; a += L) {
+      double n0 = Ph[4 * a] * xi[0] + Ph[4 * a + 1] * xi[1] + ev[4 * s + a];
+      double n1 = Ph[4 * a + 2] * xi[2] + Ph[4 * a + 3] * xi[3];
+      const double* ga = Gam + a * W + s * S;
+      const double* vv = du + s * S;
+      int j = 0;
+      for (; j + 1 < S; j += 2) {
+        n0 += ga[j] * vv[j];
+        n1 += ga[j + 1] * vv[j + 1];
+      }
+      if (j < S) n0 += ga[j] * vv[j];
+      dxs[4 * (s + 1) + a] = n0 + n1;
+    }
+    CPMPC_GSYNC();
+#pragma unroll
+    for (int a = 0; a < 4; ++a) xi[a] = dxs[4 * (s + 1) + a];
+    xi[4] = du[s * S + S - 1];
+  }
+  return true;
 }
 
 struct SolveResult {
@@ -232,8 +527,8 @@ struct SolveResult {
 // ---------------------------------------------------------------------------------------------------------------------
 // The whole Optimization::Step for one instance, executed by the L lanes of a group.  `active` is group-uniform;
 // inactive groups only take part in the warp-wide votes that keep the groups of a warp in lock step.
-// On entry the shooting state x(0) and the control guess are in shared memory (xs[0..3], u[]); on exit xs/u hold the
-// solution.
+// On entry the shooting states, the chunk-start states and the control guess are in shared memory (xs, xk, u); on
+// exit xs/u hold the solution.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int L>
 __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, const DynConst& P, const Weights& w,
@@ -244,17 +539,17 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
   double* u = c.sm + k.off_u;
   double* xc = c.sm + k.off_xc;
   double* uc = c.sm + k.off_uc;
+  double* xk = c.sm + k.off_xk;
+  double* xkc = c.sm + k.off_xkc;
   double* dxs = c.sm + k.off_dxs;
   double* du = c.sm + k.off_du;
   double* Phi = c.sm + k.off_phi;
+  double* PhiC = c.sm + k.off_phic;
   double* ev = c.sm + k.off_e;
   double* Gam = c.sm + k.off_gam;
-  double* gdu = c.sm + k.off_gdu;
-  double* tl = c.sm + k.off_tl;
-  double* tinv = c.sm + k.off_tinv;
   constexpr double half_pi = 1.5707963267948966;
   const double target[4] = {set_point, half_pi, 0.0, 0.0};
-  const int W = k.W, S = k.S, NS = k.NS, nseg = k.nseg;
+  const int W = k.W, S = k.S, NS = k.NS, nseg = k.nseg, cps = k.cps;
 
   bool active = active_in;
   double lambda = 0.0;  // params.lambda_initial (nonlinear.hpp:104)
@@ -262,7 +557,6 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
   int opt_state = OS_NOMINAL;
   double cur_f = 0.0, cur_eq = 0.0;  // Errors at the current variables
   bool have_cur = false;
-  bool tri_valid = false;  // factorisation of T for lambda == 0 is cached across iterations
   res.termination = TS_MAX_ITERATIONS;
   res.n_iter = 0;
   res.n_ls = 0;
@@ -273,20 +567,22 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
     if (!__any_sync(0xffffffffu, active)) break;
 
     double f0 = 0.0, eq0 = 0.0, d_f = 0.0, d_eq = 0.0;
-    bool qp_ok = true;
     const double lambda_in = lambda;
 
     if (active) {
-      // ---- linearise: RK4 with the Jacobian chain, forward-mode accumulation inside the segment -----------------
+      // ---- linearise: one chunk of consecutive knots per lane, RK4 with the Jacobian chain in forward mode -------
       double eq_part = 0.0;
-      for (int s = c.gl; s < nseg; s += L) {
-        double x[4] = {xs[4 * s], xs[4 * s + 1], xs[4 * s + 2], xs[4 * s + 3]};
-        double* Ph = Phi + 16 * s;
-        for (int i = 0; i < S; ++i) {
+      for (int id = c.gl; id < k.nchunk; id += L) {
+        const int s = id / cps, cc = id - s * cps;
+        const int i0 = (cc * S) / cps, i1 = ((cc + 1) * S) / cps;
+        const double* x0 = (cc == 0) ? (xs + 4 * s) : (xk + 4 * id);
+        double x[4] = {x0[0], x0[1], x0[2], x0[3]};
+        double* Ph = (cps == 1) ? (Phi + 16 * s) : (PhiC + 16 * id);
+        for (int i = i0; i < i1; ++i) {
           double A[16], Bv[4];
           const int col = s * S + i;
           rk4_step_jac(P, x, u[col], k.dt, A, Bv);
-          if (i == 0) {
+          if (i == i0) {
 #pragma unroll
             for (int q = 0; q < 16; ++q) Ph[q] = A[q];
           } else {
@@ -300,8 +596,8 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
                                A[4 * r + 3] * Ph[12 + j];
 #pragma unroll
             for (int q = 0; q < 16; ++q) Ph[q] = T[q];
-            // Gamma_j <- A Gamma_j for the earlier knots of this segment
-            for (int j = s * S; j < col; ++j) {
+            // Gamma_j <- A Gamma_j for the earlier knots of this chunk
+            for (int j = s * S + i0; j < col; ++j) {
               const double g0 = Gam[j], g1 = Gam[W + j], g2 = Gam[2 * W + j], g3 = Gam[3 * W + j];
 #pragma unroll
               for (int r = 0; r < 4; ++r)
@@ -311,14 +607,75 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
 #pragma unroll
           for (int r = 0; r < 4; ++r) Gam[r * W + col] = Bv[r];
         }
-        x[1] = mod_pi(x[1]);
-        const double* xn = xs + 4 * (s + 1);
-        const double e0 = x[0] - xn[0], e1 = mod_pi(x[1] - xn[1]), e2 = x[2] - xn[2], e3 = x[3] - xn[3];
-        ev[4 * s] = e0;
-        ev[4 * s + 1] = e1;
-        ev[4 * s + 2] = e2;
-        ev[4 * s + 3] = e3;
-        eq_part += fabs(e0) + fabs(e1) + fabs(e2) + fabs(e3);
+        if (cc == cps - 1) {
+          x[1] = mod_pi(x[1]);
+          const double* xn = xs + 4 * (s + 1);
+          const double e0 = x[0] - xn[0], e1 = mod_pi(x[1] - xn[1]), e2 = x[2] - xn[2], e3 = x[3] - xn[3];
+          ev[4 * s] = e0;
+          ev[4 * s + 1] = e1;
+          ev[4 * s + 2] = e2;
+          ev[4 * s + 3] = e3;
+          eq_part += fabs(e0) + fabs(e1) + fabs(e2) + fabs(e3);
+        }
+      }
+      if (cps > 1) {
+        // stitch the chunks of a segment: Phi_s = Phi_{cps-1} ... Phi_0, Gamma_j <- (Phi_{cps-1} ... Phi_{cc+1}) Gamma_j
+        CPMPC_GSYNC();
+        for (int base = 0; base < k.nchunk; base += L) {  // uniform trip count: the loop body synchronises
+          const int id = base + c.gl;
+          const int s = id / cps, cc = id - s * cps;
+          const bool mine = id < k.nchunk && cc < cps - 1;
+          double Sx[16], Pr[16];
+          if (mine) {
+            const double* last = PhiC + 16 * (s * cps + cps - 1);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) Sx[q] = last[q];
+            for (int m = cps - 2; m > cc; --m) {
+              const double* Pm = PhiC + 16 * (s * cps + m);
+              double T[16];
+#pragma unroll
+              for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  T[4 * r + j] = Sx[4 * r] * Pm[j] + Sx[4 * r + 1] * Pm[4 + j] + Sx[4 * r + 2] * Pm[8 + j] +
+                                 Sx[4 * r + 3] * Pm[12 + j];
+#pragma unroll
+              for (int q = 0; q < 16; ++q) Sx[q] = T[q];
+            }
+            if (cc == 0) {
+              const double* P0 = PhiC + 16 * id;
+#pragma unroll
+              for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  Pr[4 * r + j] = Sx[4 * r] * P0[j] + Sx[4 * r + 1] * P0[4 + j] + Sx[4 * r + 2] * P0[8 + j] +
+                                  Sx[4 * r + 3] * P0[12 + j];
+            }
+          }
+          CPMPC_GSYNC();
+          if (mine) {
+            double* dst = PhiC + 16 * id;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) dst[q] = Sx[q];
+            if (cc == 0) {
+              double* ph = Phi + 16 * s;
+#pragma unroll
+              for (int q = 0; q < 16; ++q) ph[q] = Pr[q];
+            }
+          }
+        }
+        CPMPC_GSYNC();
+        for (int col = c.gl; col < W; col += L) {
+          const int s = col / S, i = col - s * S;
+          const int cc = ((i + 1) * cps - 1) / S;
+          if (cc < cps - 1) {
+            const double* Sx = PhiC + 16 * (s * cps + cc);
+            const double g0 = Gam[col], g1 = Gam[W + col], g2 = Gam[2 * W + col], g3 = Gam[3 * W + col];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+              Gam[r * W + col] = Sx[4 * r] * g0 + Sx[4 * r + 1] * g1 + Sx[4 * r + 2] * g2 + Sx[4 * r + 3] * g3;
+          }
+        }
       }
       double f_part = control_cost_partial<L>(c, w, u, u_prev);
       if (c.gl == 0) {
@@ -339,6 +696,20 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
         cur_eq = eq0;
         have_cur = true;
       }
+
+      // gradient of the control costs, c_u = J^T r (optimization.cc:270-301), parked in du[]
+      for (int col = c.gl; col < W; col += L) {
+        double g = 0.0;
+        const double uk = u[col];
+        if (w.w_r > 0.0) {
+          const double wr2 = w.w_r * w.w_r;
+          if (col + 1 < W) g += wr2 * (uk - u[col + 1]);
+          if (col > 0) g -= wr2 * (u[col - 1] - uk);
+          if (col == 0) g += wr2 * (uk - u_prev);
+        }
+        if (w.w_u > 0.0) g += (w.w_u * w.w_u) * uk;
+        du[col] = g;
+      }
       CPMPC_GSYNC();
 
       if (!isfinite(f0) || !isfinite(eq0)) {
@@ -349,238 +720,29 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
     }
 
     if (active) {
-      // ---- QP in condensed form --------------------------------------------------------------------------------
-      const bool lm = lambda > 0.0;
-      const int R = lm ? k.lm_rows : 4;
-      double* U = lm ? c.lm : (c.sm + k.off_M);                          // [R][W]
-      double* Y = lm ? (c.lm + (size_t)R * W) : (c.sm + k.off_Y);         // [R+1][W]  (last row: T^-1 g)
-      double* Gm = lm ? (c.lm + (size_t)(2 * R + 1) * W) : (c.sm + k.off_gram);  // [R][R+1] (last col: U y_g)
-      double* sig = lm ? (Gm + (size_t)R * (R + 1)) : (c.sm + k.off_sig);        // [R]
-      double* inv_d = lm ? (sig + R) : (c.sm + k.off_inv_d);                     // [R]
-      double* moff = lm ? (inv_d + R) : (c.sm + k.off_moff);                     // [R] rhs offsets
-      const int node0 = lm ? 1 : (NS - 1);  // node of row 0
-
-      // (1) factor T (one lane) and the state offsets m_s (dx at the nodes for du = 0)
-      if (c.gl == 0) {
-        if (lm || !tri_valid) qp_ok = factor_tridiagonal(k, w, lambda, tl, tinv);
-        double m[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          double d = xs[i] - x_cur[i];
-          if (i == 1) d = mod_pi(d);
-          m[i] = -d;
-        }
-        dxs[0] = m[0];
-        dxs[1] = m[1];
-        dxs[2] = m[2];
-        dxs[3] = m[3];
-        for (int s = 0; s < nseg; ++s) {
-          const double* Ph = Phi + 16 * s;
-          double n[4];
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-            n[r] = Ph[4 * r] * m[0] + Ph[4 * r + 1] * m[1] + Ph[4 * r + 2] * m[2] + Ph[4 * r + 3] * m[3] + ev[4 * s + r];
-          const int node = s + 1;
-#pragma unroll
-          for (int r = 0; r < 4; ++r) m[r] = n[r];
-          if (node >= node0) {
-            const int row = 4 * (node - node0);
-            const bool terminal = node == NS - 1;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              double invd, off;
-              if (terminal) {
-                double d = xs[4 * node + i] - target[i];
-                if (i == 1) d = mod_pi(d);
-                if (w.wt[i] < 0.0) {
-                  invd = 0.0;  // hard row
-                  off = m[i] + d;
-                } else {
-                  const double dd = w.wt[i] * w.wt[i] + lambda;
-                  if (dd > 0.0) {
-                    invd = 1.0 / dd;
-                    off = m[i] + (w.wt[i] * w.wt[i] * d) * invd;
-                  } else {
-                    invd = -1.0;  // inactive row
-                    off = 0.0;
-                  }
-                }
-              } else {
-                invd = 1.0 / lambda;
-                off = m[i];
-              }
-              inv_d[row + i] = invd;
-              moff[row + i] = off;
-            }
-          }
-        }
-      }
-      tri_valid = !lm;
-
-      // (2) rows of U: sensitivities of the node states to the controls, propagated through later segments
-      for (int s = c.gl; s < nseg; s += L) {
-        for (int i = 0; i < S; ++i) {
-          const int col = s * S + i;
-          double v[4] = {Gam[col], Gam[W + col], Gam[2 * W + col], Gam[3 * W + col]};
-          if (lm) {
-            for (int node = 1; node <= s; ++node)
-#pragma unroll
-              for (int r = 0; r < 4; ++r) {
-                U[(size_t)(4 * (node - 1) + r) * W + col] = 0.0;
-                Y[(size_t)(4 * (node - 1) + r) * W + col] = 0.0;
-              }
-          }
-          for (int node = s + 1; node <= NS - 1; ++node) {
-            if (node > s + 1) {
-              const double* Ph = Phi + 16 * (node - 1);
-              double n[4];
-#pragma unroll
-              for (int r = 0; r < 4; ++r)
-                n[r] = Ph[4 * r] * v[0] + Ph[4 * r + 1] * v[1] + Ph[4 * r + 2] * v[2] + Ph[4 * r + 3] * v[3];
-#pragma unroll
-              for (int r = 0; r < 4; ++r) v[r] = n[r];
-            }
-            if (node >= node0) {
-#pragma unroll
-              for (int r = 0; r < 4; ++r) {
-                U[(size_t)(4 * (node - node0) + r) * W + col] = v[r];
-                Y[(size_t)(4 * (node - node0) + r) * W + col] = v[r];
-              }
-            }
-          }
-          // gradient of the control costs, c_u = J^T r (optimization.cc:270-301)
-          double g = 0.0;
-          const double uk = u[col];
-          if (w.w_r > 0.0) {
-            const double wr2 = w.w_r * w.w_r;
-            if (col + 1 < W) g += wr2 * (uk - u[col + 1]);
-            if (col > 0) g -= wr2 * (u[col - 1] - uk);
-            if (col == 0) g += wr2 * (uk - u_prev);
-          }
-          if (w.w_u > 0.0) g += (w.w_u * w.w_u) * uk;
-          Y[(size_t)R * W + col] = g;
-          du[col] = g;  // keep c_u for the directional derivative
-        }
-      }
-      CPMPC_GSYNC();
-      qp_ok = __shfl_sync(c.gmask, qp_ok ? 1 : 0, (c.gmask == 0xffffffffu) ? 0 : (__ffs(c.gmask) - 1)) != 0;
-
-      // (3) Y_r = T^-1 U_r^T and y_g = T^-1 g
-      for (int r = c.gl; r <= R; r += L) solve_tridiagonal(W, tl, tinv, Y + (size_t)r * W);
-      CPMPC_GSYNC();
-
-      // (4) Schur complement  Gm[i][j] = U_i . Y_j  (j == R: U_i . y_g)
-      for (int j = c.gl; j <= R; j += L) {
-        const double* yj = Y + (size_t)j * W;
-        for (int i = 0; i < R; ++i) {
-          const double* ui = U + (size_t)i * W;
-          double acc = 0.0;
-          for (int q = 0; q < W; ++q) acc += ui[q] * yj[q];
-          Gm[(size_t)i * (R + 1) + j] = acc;
-        }
-      }
-      CPMPC_GSYNC();
-
-      // (5) Cholesky of (Gm + diag(1/d)) and solve for the row multipliers (one lane)
-      if (c.gl == 0 && qp_ok) {
-        const int ld = R + 1;
-        for (int i = 0; i < R; ++i) {
-          if (inv_d[i] < 0.0) {
-            for (int j = 0; j < R; ++j) {
-              Gm[(size_t)i * ld + j] = 0.0;
-              Gm[(size_t)j * ld + i] = 0.0;
-            }
-            Gm[(size_t)i * ld + i] = 1.0;
-            sig[i] = 0.0;
-          } else {
-            Gm[(size_t)i * ld + i] += inv_d[i];
-            sig[i] = moff[i] - Gm[(size_t)i * ld + R];
-          }
-        }
-        for (int j = 0; j < R && qp_ok; ++j) {
-          double d = Gm[(size_t)j * ld + j];
-          for (int q = 0; q < j; ++q) d -= Gm[(size_t)j * ld + q] * Gm[(size_t)j * ld + q];
-          if (!(d > 0.0)) {
-            qp_ok = false;
-            break;
-          }
-          d = sqrt(d);
-          Gm[(size_t)j * ld + j] = d;
-          const double inv = 1.0 / d;
-          for (int i = j + 1; i < R; ++i) {
-            double sacc = Gm[(size_t)i * ld + j];
-            for (int q = 0; q < j; ++q) sacc -= Gm[(size_t)i * ld + q] * Gm[(size_t)j * ld + q];
-            Gm[(size_t)i * ld + j] = sacc * inv;
-          }
-        }
-        if (qp_ok) {
-          for (int i = 0; i < R; ++i) {
-            double sacc = sig[i];
-            for (int q = 0; q < i; ++q) sacc -= Gm[(size_t)i * ld + q] * sig[q];
-            sig[i] = sacc / Gm[(size_t)i * ld + i];
-          }
-          for (int i = R - 1; i >= 0; --i) {
-            double sacc = sig[i];
-            for (int q = i + 1; q < R; ++q) sacc -= Gm[(size_t)q * ld + i] * sig[q];
-            sig[i] = sacc / Gm[(size_t)i * ld + i];
-          }
-        }
-      }
-      CPMPC_GSYNC();
-      qp_ok = __shfl_sync(c.gmask, qp_ok ? 1 : 0, (c.gmask == 0xffffffffu) ? 0 : (__ffs(c.gmask) - 1)) != 0;
-
+      // ---- QP step (qp.cc:679-729) -----------------------------------------------------------------------------
+      double cdx = 0.0;
+      const bool qp_ok = riccati_qp<L>(c, w, lambda, x_cur, target, cdx);
       if (!qp_ok) {
         // QP_INDEFINITE: Solve() returns before this iteration is logged (nonlinear.cc:103-105)
         res.termination = TS_QP_INDEFINITE;
         active = false;
       } else {
-        // (6) du = -y_g - sum_r sig_r Y_r ; partial sums of c.dx and dx^T G dx over this lane's columns
-        double cdx = 0.0;
-        for (int s = c.gl; s < nseg; s += L) {
-          double acc[4] = {0.0, 0.0, 0.0, 0.0};
-          for (int i = 0; i < S; ++i) {
-            const int col = s * S + i;
-            double v = -Y[(size_t)R * W + col];
-            for (int r = 0; r < R; ++r) v -= sig[r] * Y[(size_t)r * W + col];
-            cdx += du[col] * v;  // du[] still holds c_u
-            du[col] = v;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) acc[r] += Gam[r * W + col] * v;
-          }
-#pragma unroll
-          for (int r = 0; r < 4; ++r) gdu[4 * s + r] = acc[r];
-        }
-        CPMPC_GSYNC();
-
-        // (7) state steps by forward propagation; quadratic form; directional derivatives (nonlinear.cc:457-502)
+        // quadratic form dx^T G dx and the directional derivatives (nonlinear.cc:457-502)
         double quad = 0.0;
         const double wu2 = w.w_u * w.w_u, wr2 = w.w_r * w.w_r;
-        for (int s = c.gl; s < nseg; s += L) {
-          for (int i = 0; i < S; ++i) {
-            const int col = s * S + i;
-            const double a = wu2 + lambda + wr2 * ((col + 1 < W) ? 2.0 : 1.0);
-            const double v = du[col];
-            quad += a * v * v;
-            if (col + 1 < W) quad -= 2.0 * wr2 * v * du[col + 1];
-          }
+        for (int col = c.gl; col < W; col += L) {
+          const double a = wu2 + lambda + wr2 * ((col + 1 < W) ? 2.0 : 1.0);
+          const double v = du[col];
+          quad += a * v * v;
+          if (col + 1 < W) quad -= 2.0 * wr2 * v * du[col + 1];
+        }
+        for (int q = c.gl; q < NS; q += L) {
+          const double* m = dxs + 4 * q;
+          quad += lambda * (m[0] * m[0] + m[1] * m[1] + m[2] * m[2] + m[3] * m[3]);
         }
         if (c.gl == 0) {
-          double m[4] = {dxs[0], dxs[1], dxs[2], dxs[3]};
-          quad += lambda * (m[0] * m[0] + m[1] * m[1] + m[2] * m[2] + m[3] * m[3]);
-          for (int s = 0; s < nseg; ++s) {
-            const double* Ph = Phi + 16 * s;
-            double n[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-              n[r] = Ph[4 * r] * m[0] + Ph[4 * r + 1] * m[1] + Ph[4 * r + 2] * m[2] + Ph[4 * r + 3] * m[3] +
-                     gdu[4 * s + r] + ev[4 * s + r];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              m[r] = n[r];
-              dxs[4 * (s + 1) + r] = n[r];
-            }
-            quad += lambda * (m[0] * m[0] + m[1] * m[1] + m[2] * m[2] + m[3] * m[3]);
-          }
+          const double* m = dxs + 4 * (NS - 1);
           // terminal rows: cost gradient / Hessian, and the equality rows' A_i.dx
           double deq_term = 0.0;
 #pragma unroll
@@ -664,13 +826,10 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
           xc[4 * q + 2] = __dadd_rn(xs[4 * q + 2], __dmul_rn(dxs[4 * q + 2], alpha));
           xc[4 * q + 3] = __dadd_rn(xs[4 * q + 3], __dmul_rn(dxs[4 * q + 3], alpha));
         }
-        for (int s = c.gl; s < nseg; s += L)
-          for (int i = 0; i < S; ++i) {
-            const int col = s * S + i;
-            uc[col] = clampd(__dadd_rn(u[col], __dmul_rn(du[col], alpha)), -k.u_clamp, k.u_clamp);
-          }
+        for (int col = c.gl; col < W; col += L)
+          uc[col] = clampd(__dadd_rn(u[col], __dmul_rn(du[col], alpha)), -k.u_clamp, k.u_clamp);
         CPMPC_GSYNC();
-        evaluate_errors<L>(c, P, w, xc, uc, x_cur, set_point, u_prev, step_f, step_eq);
+        evaluate_errors<L>(c, P, w, xc, uc, xkc, x_cur, set_point, u_prev, step_f, step_eq);
         CPMPC_GSYNC();
         if (lrow != nullptr && c.gl == 0 && n_steps < 6) {
           lrow[9 + 3 * n_steps] = alpha;
@@ -704,12 +863,10 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
     if (active) {
       bool exit_now = false;
       if (step_result == SR_SUCCESS) {
-        for (int q = c.gl; q < NS; q += L) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) xs[4 * q + i] = xc[4 * q + i];
-        }
-        for (int s = c.gl; s < nseg; s += L)
-          for (int i = 0; i < S; ++i) u[s * S + i] = uc[s * S + i];
+        for (int q = c.gl; q < 4 * NS; q += L) xs[q] = xc[q];
+        for (int col = c.gl; col < W; col += L) u[col] = uc[col];
+        if (cps > 1)
+          for (int q = c.gl; q < 4 * k.nchunk; q += L) xk[q] = xkc[q];
         CPMPC_GSYNC();
         lambda = fmax(lambda * ((opt_state == OS_RESTORE_LM) ? k.lam_dec_restore : k.lam_dec_success), k.lam_min);
         opt_state = OS_NOMINAL;
@@ -766,8 +923,8 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
 // Kernel: persistent grid-stride over instances; each warp carries 32/L instances at a time.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int L>
-__global__ void __launch_bounds__(128, 1) cpmpc_solve_kernel(const KernelCfg cfg, const KernelIO io) {
-  const int WARPS_PER_BLOCK = blockDim.x >> 5;  // 1, 2 or 4: one warp per SM sub-partition
+__global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg, const KernelIO io) {
+  const int WARPS_PER_BLOCK = blockDim.x >> 5;  // up to 8: two warps per SM sub-partition
   extern __shared__ double smem[];
   constexpr int G = 32 / L;
   const int lane = threadIdx.x & 31;
@@ -780,7 +937,7 @@ __global__ void __launch_bounds__(128, 1) cpmpc_solve_kernel(const KernelCfg cfg
   const long long group_id = ((long long)blockIdx.x * WARPS_PER_BLOCK + warp) * G + g;
   const long long n_groups = (long long)gridDim.x * WARPS_PER_BLOCK * G;
   c.sm = smem + (size_t)(warp * G + g) * cfg.stride;
-  c.lm = io.lm_scratch + (size_t)group_id * cfg.lm_stride;
+  c.kk = io.kk_scratch + (size_t)group_id * cfg.kk_stride;
   const int W = cfg.W, S = cfg.S, NS = cfg.NS, N = cfg.N;
   double* xs = c.sm + cfg.off_xs;
   double* u = c.sm + cfg.off_u;
@@ -834,12 +991,23 @@ __global__ void __launch_bounds__(128, 1) cpmpc_solve_kernel(const KernelCfg cfg
         }
         CPMPC_GSYNC();
         if (c.gl == 0) {
-          // FillInitialGuess: all shooting states re-integrated from x(0) (optimization.cc:333-351)
+          // FillInitialGuess: all shooting states re-integrated from x(0) (optimization.cc:333-351); the states at
+          // the chunk boundaries inside a segment are kept for the first linearisation
           double x[4] = {x_cur[0], x_cur[1], x_cur[2], x_cur[3]};
+          double* xk = c.sm + cfg.off_xk;
 #pragma unroll
           for (int i = 0; i < 4; ++i) xs[i] = x[i];
           for (int s = 1; s < NS; ++s) {
+            int cc = 1;
+            int nb = (cfg.cps > 1) ? (S / cfg.cps) : S;
             for (int i = 0; i < S; ++i) {
+              if (i == nb) {
+                double* dst = xk + 4 * ((s - 1) * cfg.cps + cc);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dst[q] = x[q];
+                ++cc;
+                nb = (cc < cfg.cps) ? (cc * S) / cfg.cps : S;
+              }
               rk4_step<false>(P, x, u[(s - 1) * S + i], cfg.dt);
               x[1] = mod_pi(x[1]);
             }
