@@ -114,7 +114,9 @@ void BuildLayout(KernelCfg& k) {
   k.off_xkc = k.off_uc + W;
   // Riccati stage matrix over (S controls | xi | rho), packed lower triangle
   const int D = S + NCOL_MAX;
-  k.off_aug = take(D * (D + 1) / 2);
+  const int n_ric = D * (D + 1) / 2;
+  const int n_cond = k.condensed ? 6 * W : 0;  // condensed QP scratch: Z [4][W], tl [W], tinv [W]
+  k.off_aug = take(n_ric > n_cond ? n_ric : n_cond);
   k.off_vbuf = take(25 + XI_DIM * NR_MAX);
   k.off_invd = take(S);
   // odd stride (in doubles) so that the same field of neighbouring instances falls into different banks
@@ -262,6 +264,13 @@ int cpmpc_create(const cpmpc_params* params, int64_t batch, int device, cpmpc_ha
   if (const char* env = std::getenv("CPMPC_CHUNKS")) {
     const int v = std::atoi(env);
     if (v >= 1 && v <= k.S && v * k.nseg <= lanes) k.cps = v;
+  }
+  // QP method for the undamped iterations: condensed while the horizon is short enough for open-loop sensitivity
+  // products to stay accurate, Riccati beyond (and always for Levenberg-Marquardt iterations)
+  k.condensed = (k.W * k.dt <= 0.6) ? 1 : 0;
+  if (const char* env = std::getenv("CPMPC_QP")) {
+    if (std::strcmp(env, "riccati") == 0) k.condensed = 0;
+    if (std::strcmp(env, "condensed") == 0) k.condensed = 1;
   }
   BuildLayout(k);
   const int groups_per_warp = 32 / lanes;

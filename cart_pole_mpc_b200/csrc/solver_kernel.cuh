@@ -39,6 +39,7 @@ constexpr int NCOL_MAX = XI_DIM + NR_MAX;
 
 struct KernelCfg {
   int W, S, NS, nseg, N, max_iter, max_ls;
+  int condensed;  // 1: lambda == 0 iterations use the condensed QP (short horizons), 0: always Riccati
   int cps;     // chunks per shooting segment in the linearisation
   int nchunk;  // nseg * cps
   int stride;  // doubles of shared memory per instance
@@ -215,14 +216,45 @@ __device__ __forceinline__ void evaluate_errors(const Ctx& c, const DynConst& P,
   eq_out = group_sum<L>(eq, c.gmask);
 }
 
-// Packed lower-triangular index.
-__device__ __forceinline__ int tri(const int r, const int col) { return ((r * (r + 1)) >> 1) + col; }
+// Column-major packed lower-triangular index of a D x D matrix: column c holds rows c..D-1 contiguously.
+__device__ __forceinline__ int cbase(const int D, const int col) { return col * D - ((col * (col - 1)) >> 1) - col; }
+// aug[cbase(D, col) + r] is entry (r, col), r >= col.
+
+// y[0..n) -= a * x[0..n) on shared memory.  Loads are issued in batches ahead of the stores so that the LDS latency
+// is paid once per batch (x and y never overlap, which the compiler cannot know).
+__device__ __forceinline__ void axpy_neg(double* y, const double* x, const double a, const int n) {
+  int r = 0;
+  for (; r + 4 <= n; r += 4) {
+    const double x0 = x[r], x1 = x[r + 1], x2 = x[r + 2], x3 = x[r + 3];
+    const double y0 = y[r], y1 = y[r + 1], y2 = y[r + 2], y3 = y[r + 3];
+    y[r] = fma(-a, x0, y0);
+    y[r + 1] = fma(-a, x1, y1);
+    y[r + 2] = fma(-a, x2, y2);
+    y[r + 3] = fma(-a, x3, y3);
+  }
+  if (r + 2 <= n) {
+    const double x0 = x[r], x1 = x[r + 1];
+    const double y0 = y[r], y1 = y[r + 1];
+    y[r] = fma(-a, x0, y0);
+    y[r + 1] = fma(-a, x1, y1);
+    r += 2;
+  }
+  if (r < n) y[r] = fma(-a, x[r], y[r]);
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Equality-constrained QP of one SQP iteration (reference: QPNullSpaceSolver::Solve, qp.cc:679-729) by a segment-wise
 // Riccati recursion; see the header comment.  On entry Phi / Gam / ev hold the segment blocks, du[] the gradient of
 // the control costs.  On exit du[] and dxs[] hold the step; returns false when a pivot is not positive (the reduced
 // Hessian is not positive definite: QP_INDEFINITE).  `cdx` returns this lane's share of c_u . du.
+//
+// Stage matrix (column-major packed lower triangle, D = S + 5 + nr):
+//        [ H_vv                     ]   v   : the S controls of the segment
+//    A = [ H_xv   H_xx              ]   xi  : (dx_s, previous control)
+//        [ h_v^T  h_x^T    C        ]   rho : (1, mu_1 .. mu_nh)
+// S steps of right-looking LDL^T elimination (no square roots: column j stays unscaled, its pivot reciprocal goes to
+// invd[j]) leave the next value function in the trailing (xi, rho) block and Z = L^-1 [H_vx h_v] in rows S.. of the
+// first S columns; the gains K = L^-T D^-1 Z follow by back-substitution.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int L>
 __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights& w, const double lambda,
@@ -265,8 +297,9 @@ __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights& w, const
   }
 
   // terminal value function V_N over (xi | rho), stored where a stage elimination leaves it: rows/cols S..D-1
-  for (int a = c.gl; a < n2; a += L) {
-    for (int b = 0; b <= a; ++b) {
+  for (int b = c.gl; b < n2; b += L) {
+    double* colp = aug + cbase(D, S + b) + S;  // entry (S + a, S + b) at colp[a]
+    for (int a = b; a < n2; ++a) {
       double v = 0.0;
       if (a < 4) {
         if (a == b) {
@@ -282,42 +315,45 @@ __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights& w, const
         const int hj = (j == 0) ? hcomp[0] : (j == 1) ? hcomp[1] : (j == 2) ? hcomp[2] : hcomp[3];
         v = (b == hj) ? 1.0 : 0.0;
       }
-      aug[tri(S + a, S + b)] = v;
+      colp[a] = v;
     }
   }
   CPMPC_GSYNC();
 
+  // trailing-block accessor: entry (S + a, S + b), a >= b
+#define CPMPC_TR(a, b) aug[cbase(D, S + (b)) + S + (a)]
   bool ok = true;
-  for (int s = nseg - 1; s >= 0 && ok; --s) {
+  for (int s = nseg - 1; s >= 0; --s) {
     const double* Ph = Phi + 16 * s;
     const double f0 = ev[4 * s], f1 = ev[4 * s + 1], f2 = ev[4 * s + 2], f3 = ev[4 * s + 3];
     // (i) snapshot P (full 5x5) and q = p + (P f) e_0; fold f . p_r into the rho-rho column 0 (in place)
     for (int t = c.gl; t < 25 + XI_DIM * nr + nh; t += L) {
       if (t < 25) {
         const int a = t / 5, b = t - 5 * a;
-        vb[t] = (a >= b) ? aug[tri(S + a, S + b)] : aug[tri(S + b, S + a)];
+        vb[t] = (a >= b) ? CPMPC_TR(a, b) : CPMPC_TR(b, a);
       } else if (t < 25 + XI_DIM * nr) {
         const int t2 = t - 25;
         const int r = t2 / XI_DIM, a = t2 - XI_DIM * r;
-        double v = aug[tri(S + XI_DIM + r, S + a)];
+        double v = CPMPC_TR(XI_DIM + r, a);
         if (r == 0) {
-          const double p0 = (a >= 0) ? aug[tri(S + a, S + 0)] : 0.0;
-          const double p1 = (a >= 1) ? aug[tri(S + a, S + 1)] : aug[tri(S + 1, S + a)];
-          const double p2 = (a >= 2) ? aug[tri(S + a, S + 2)] : aug[tri(S + 2, S + a)];
-          const double p3 = (a >= 3) ? aug[tri(S + a, S + 3)] : aug[tri(S + 3, S + a)];
+          const double p0 = CPMPC_TR(a, 0);
+          const double p1 = (a >= 1) ? CPMPC_TR(a, 1) : CPMPC_TR(1, a);
+          const double p2 = (a >= 2) ? CPMPC_TR(a, 2) : CPMPC_TR(2, a);
+          const double p3 = (a >= 3) ? CPMPC_TR(a, 3) : CPMPC_TR(3, a);
           v += p0 * f0 + p1 * f1 + p2 * f2 + p3 * f3;
         }
         qb[a * NR_MAX + r] = v;
       } else {
         const int r = t - 25 - XI_DIM * nr + 1;  // 1..nh
-        const double* pr = aug + tri(S + XI_DIM + r, S);
-        aug[tri(S + XI_DIM + r, S + XI_DIM)] += pr[0] * f0 + pr[1] * f1 + pr[2] * f2 + pr[3] * f3;
+        CPMPC_TR(XI_DIM + r, XI_DIM) += CPMPC_TR(XI_DIM + r, 0) * f0 + CPMPC_TR(XI_DIM + r, 1) * f1 +
+                                        CPMPC_TR(XI_DIM + r, 2) * f2 + CPMPC_TR(XI_DIM + r, 3) * f3;
       }
     }
     CPMPC_GSYNC();
 
-    // (ii) assemble the stage matrix, one column per lane
+    // (ii) assemble the stage matrix: every lane writes whole columns (contiguous)
     for (int t = c.gl; t < S + XI_DIM; t += L) {
+      double* colp = aug + cbase(D, t);  // entry (r, t) at colp[r]
       if (t < S) {
         const int j = t, col = s * S + j;
         const double g0 = Gam[col], g1 = Gam[W + col], g2 = Gam[2 * W + col], g3 = Gam[3 * W + col];
@@ -332,17 +368,17 @@ __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights& w, const
           if (i == S - 1) v += PG[4];
           if (i == j) v += wu2 + lambda + wr2 * ((col + 1 < W) ? 2.0 : 1.0);
           if (i == j + 1) v -= wr2;
-          aug[tri(i, j)] = v;
+          colp[i] = v;
         }
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc)
-          aug[tri(S + cc, j)] = Ph[cc] * PG[0] + Ph[4 + cc] * PG[1] + Ph[8 + cc] * PG[2] + Ph[12 + cc] * PG[3];
-        aug[tri(S + 4, j)] = (j == 0 && s > 0) ? -wr2 : 0.0;
+          colp[S + cc] = Ph[cc] * PG[0] + Ph[4 + cc] * PG[1] + Ph[8 + cc] * PG[2] + Ph[12 + cc] * PG[3];
+        colp[S + 4] = (j == 0 && s > 0) ? -wr2 : 0.0;
         for (int r = 0; r < nr; ++r) {
           double v = g0 * qb[r] + g1 * qb[NR_MAX + r] + g2 * qb[2 * NR_MAX + r] + g3 * qb[3 * NR_MAX + r] +
                      g4 * qb[4 * NR_MAX + r];
           if (r == 0) v += du[col];
-          aug[tri(S + XI_DIM + r, j)] = v;
+          colp[S + XI_DIM + r] = v;
         }
       } else {
         const int cc = t - S;  // xi column
@@ -354,52 +390,81 @@ __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights& w, const
           for (int c2 = cc; c2 < 4; ++c2) {
             double v = Ph[c2] * PF[0] + Ph[4 + c2] * PF[1] + Ph[8 + c2] * PF[2] + Ph[12 + c2] * PF[3];
             if (c2 == cc && s > 0) v += lambda;
-            aug[tri(S + c2, S + cc)] = v;
+            colp[S + c2] = v;
           }
-          aug[tri(S + 4, S + cc)] = 0.0;
+          colp[S + 4] = 0.0;
           for (int r = 0; r < nr; ++r)
-            aug[tri(S + XI_DIM + r, S + cc)] =
-                h0 * qb[r] + h1 * qb[NR_MAX + r] + h2 * qb[2 * NR_MAX + r] + h3 * qb[3 * NR_MAX + r];
+            colp[S + XI_DIM + r] = h0 * qb[r] + h1 * qb[NR_MAX + r] + h2 * qb[2 * NR_MAX + r] + h3 * qb[3 * NR_MAX + r];
         } else {
-          aug[tri(S + 4, S + 4)] = 0.0;
-          for (int r = 0; r < nr; ++r) aug[tri(S + XI_DIM + r, S + 4)] = 0.0;
+          colp[S + 4] = 0.0;
+          for (int r = 0; r < nr; ++r) colp[S + XI_DIM + r] = 0.0;
         }
       }
     }
     CPMPC_GSYNC();
 
-    // (iii) eliminate the S controls: right-looking Cholesky steps over the whole D x D matrix
+    // (iii) eliminate the S controls: right-looking LDL^T steps over the whole D x D matrix, one trailing column per
+    // lane.  The lane that owns column j + 1 handles it first and publishes the reciprocal of the next pivot.
+    if (c.gl == 0) {
+      const double piv = aug[0];
+      invd[0] = (piv > 0.0) ? fm::rcp(piv) : -1.0;
+    }
+    CPMPC_GSYNC();
     for (int j = 0; j < S; ++j) {
-      const double piv = aug[tri(j, j)];
-      if (!(piv > 0.0)) {
+      const double rd = invd[j];
+      if (!(rd > 0.0)) {
         ok = false;
         break;
       }
-      double root, inv;
-      fm::sqrt_rsqrt(piv, root, inv);
-      if (c.gl == 0) invd[j] = inv;
-      for (int r = j + 1 + c.gl; r < D; r += L) aug[tri(r, j)] *= inv;
-      CPMPC_GSYNC();
-      for (int r = j + 1 + c.gl; r < D; r += L) {
-        double* row = aug + tri(r, 0);
-        const double lrj = row[j];
-        for (int cc = j + 1; cc <= r; ++cc) row[cc] -= lrj * aug[tri(cc, j)];
+      const double* colj = aug + cbase(D, j);  // (r, j) at colj[r]
+      for (int cc = j + 1 + c.gl; cc < D; cc += L) {
+        double* colc = aug + cbase(D, cc);
+        const double l = colj[cc] * rd;
+        if (cc == j + 1 && cc < S) {
+          // next pivot first, so that its reciprocal is ready when the others reach the barrier
+          const double piv = fma(-l, colj[cc], colc[cc]);
+          colc[cc] = piv;
+          invd[cc] = (piv > 0.0) ? fm::rcp(piv) : -1.0;
+          axpy_neg(colc + cc + 1, colj + cc + 1, l, D - cc - 1);
+        } else {
+          axpy_neg(colc + cc, colj + cc, l, D - cc);
+        }
       }
       CPMPC_GSYNC();
     }
     if (!ok) break;
 
-    // (iv) gains: rows S.. of the panel hold (L^-1 B)^T; back-substitute to (H_vv^-1 B)^T in place, then spill
+    // (iv) gains: row S + q of the panel holds Z[:, q]; x_j = rd_j (z_j - sum_{i > j} U[i][j] x_i) in place, the
+    // next unknown carried in a register so the chain does not go through shared memory.  Then spill to global.
     for (int q = c.gl; q < n2; q += L) {
-      double* row = aug + tri(S + q, 0);
-      for (int j = S - 1; j >= 0; --j) {
-        const double xj = row[j] * invd[j];
-        row[j] = xj;
-        const double* Lj = aug + tri(j, 0);
-        for (int i = 0; i < j; ++i) row[i] -= Lj[i] * xj;
-      }
+      const int rq = S + q;
       double* dst = c.kk + ((size_t)s * NCOL_MAX + q) * S;
-      for (int j = 0; j < S; ++j) __stcg(dst + j, row[j]);
+      double nxt = aug[cbase(D, S - 1) + rq];
+      for (int j = S - 1; j >= 0; --j) {
+        const double xj = nxt * invd[j];
+        __stcg(dst + j, xj);
+        if (j == 0) break;
+        // row j of U: entries (j, i) for i < j live in column i
+        const double* pi = aug + cbase(D, j - 1);  // column j - 1
+        nxt = fma(-pi[j], xj, pi[rq]);
+        // remaining columns i = j-2 .. 0, four at a time with the loads ahead of the stores
+        int i = j - 2;
+        int o = cbase(D, j - 1);  // offset of column i + 1; cbase(i) = cbase(i + 1) - (D - i - 1)
+        for (; i >= 3; i -= 4) {
+          const int o0 = o - (D - i - 1), o1 = o0 - (D - i), o2 = o1 - (D - i + 1), o3 = o2 - (D - i + 2);
+          const double u0 = aug[o0 + j], u1 = aug[o1 + j], u2 = aug[o2 + j], u3 = aug[o3 + j];
+          const double z0 = aug[o0 + rq], z1 = aug[o1 + rq], z2 = aug[o2 + rq], z3 = aug[o3 + rq];
+          aug[o0 + rq] = fma(-u0, xj, z0);
+          aug[o1 + rq] = fma(-u1, xj, z1);
+          aug[o2 + rq] = fma(-u2, xj, z2);
+          aug[o3 + rq] = fma(-u3, xj, z3);
+          o = o3;
+        }
+        for (; i >= 0; --i) {
+          o -= (D - i - 1);
+          aug[o + rq] = fma(-aug[o + j], xj, aug[o + rq]);
+        }
+      }
     }
     CPMPC_GSYNC();
   }
@@ -423,13 +488,14 @@ __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights& w, const
 #pragma unroll
       for (int q = 0; q < 4; ++q) Mh[j][q] = (j == q) ? 1.0 : 0.0;
       if (j < nh) {
-        const double* pr = aug + tri(S + XI_DIM + 1 + j, S);
+        const int rj = XI_DIM + 1 + j;
         const int hj = hcomp[j];
         const double dj = (hj == 0) ? dT[0] : (hj == 1) ? dT[1] : (hj == 2) ? dT[2] : dT[3];
-        rhs[j] = pr[0] * m0[0] + pr[1] * m0[1] + pr[2] * m0[2] + pr[3] * m0[3] + pr[XI_DIM] + dj;
+        rhs[j] = CPMPC_TR(rj, 0) * m0[0] + CPMPC_TR(rj, 1) * m0[1] + CPMPC_TR(rj, 2) * m0[2] +
+                 CPMPC_TR(rj, 3) * m0[3] + CPMPC_TR(rj, XI_DIM) + dj;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (q <= j) Mh[j][q] = -pr[XI_DIM + 1 + q];
+          if (q <= j) Mh[j][q] = -CPMPC_TR(rj, XI_DIM + 1 + q);
       }
     }
     // Cholesky of the (nh x nh) lower triangle, rows >= nh are identity
@@ -512,6 +578,253 @@ __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights& w, const
     xi[4] = du[s * S + S - 1];
   }
   return true;
+#undef CPMPC_TR
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The same QP in condensed form, for lambda == 0 on short horizons (cfg.condensed): with the shooting states
+// eliminated forward through the linearised dynamics the Hessian over the W controls is T + U^T D U, T the
+// tridiagonal control / control-rate Hessian and U the 4 rows of the terminal-state sensitivities (soft rows carry
+// weight d = w^2, hard rows are constraints).  T = L D_T L^T is factored once per solve (O(W)); with Z = L^-1 U^T
+// the multipliers come from the 4x4 system (Z^T D_T^-1 Z + diag(1/d)) sigma = rhs, and
+// du = -L^-T D_T^-1 (z_g + Z sigma).  About 3 kflop instead of 15 kflop for the Riccati recursion, but the rows of U
+// are open-loop products of the segment transition matrices: accurate while the horizon is short (W dt of a fraction
+// of a second), useless on long unstable horizons (tests/prototypes/qp_riccati_proto.py) - the host picks.
+// Scratch (aliases the Riccati stage matrix): Z [4][W], tl [W], tinv [W].
+// ---------------------------------------------------------------------------------------------------------------------
+template <int L>
+__device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, bool& tri_valid, const double x_cur[4],
+                                             const double target[4], double& cdx) {
+  const KernelCfg& k = *c.cfg;
+  const int W = k.W, S = k.S, NS = k.NS, nseg = k.nseg;
+  const double* xs = c.sm + k.off_xs;
+  double* dxs = c.sm + k.off_dxs;
+  double* du = c.sm + k.off_du;
+  const double* Phi = c.sm + k.off_phi;
+  const double* ev = c.sm + k.off_e;
+  const double* Gam = c.sm + k.off_gam;
+  double* Z = c.sm + k.off_aug;  // [4][W]
+  double* tl = Z + 4 * W;        // sub-diagonal multipliers of the unit bidiagonal factor
+  double* tinv = tl + W;         // reciprocal pivots
+  const double wu2 = w.w_u * w.w_u, wr2 = w.w_r * w.w_r;
+  bool ok = true;
+
+  // (1) factor T once per solve (lane L-1, while the other lanes build the rows of U)
+  if (!tri_valid && c.gl == L - 1) {
+    double dprev_inv = 0.0;
+    for (int j = 0; j < W; ++j) {
+      const double a = wu2 + wr2 * ((j + 1 < W) ? 2.0 : 1.0);
+      double l = 0.0, d = a;
+      if (j > 0) {
+        l = -wr2 * dprev_inv;
+        d = fma(l, wr2, a);
+      }
+      ok = ok && (d > 0.0);
+      dprev_inv = fm::rcp(d);
+      tl[j] = l;
+      tinv[j] = dprev_inv;
+    }
+  }
+  tri_valid = true;
+  // (2) rows of U: sensitivity of the terminal node to every control, through the later segments
+  for (int col = c.gl; col < W; col += L) {
+    const int s = col / S;
+    double v0 = Gam[col], v1 = Gam[W + col], v2 = Gam[2 * W + col], v3 = Gam[3 * W + col];
+    for (int t = s + 1; t < nseg; ++t) {
+      const double* Ph = Phi + 16 * t;
+      const double n0 = Ph[0] * v0 + Ph[1] * v1 + Ph[2] * v2 + Ph[3] * v3;
+      const double n1 = Ph[4] * v0 + Ph[5] * v1 + Ph[6] * v2 + Ph[7] * v3;
+      const double n2 = Ph[8] * v0 + Ph[9] * v1 + Ph[10] * v2 + Ph[11] * v3;
+      const double n3 = Ph[12] * v0 + Ph[13] * v1 + Ph[14] * v2 + Ph[15] * v3;
+      v0 = n0;
+      v1 = n1;
+      v2 = n2;
+      v3 = n3;
+    }
+    Z[col] = v0;
+    Z[W + col] = v1;
+    Z[2 * W + col] = v2;
+    Z[3 * W + col] = v3;
+  }
+  // node steps for du = 0: m_0 = -(x_0 - x_cur), m_{s+1} = Phi_s m_s + e_s (every lane, registers)
+  double m[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double d = xs[i] - x_cur[i];
+    if (i == 1) d = mod_pi(d);
+    m[i] = -d;
+  }
+  const double m00 = m[0], m01 = m[1], m02 = m[2], m03 = m[3];
+  for (int s = 0; s < nseg; ++s) {
+    const double* Ph = Phi + 16 * s;
+    double n[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      n[r] = Ph[4 * r] * m[0] + Ph[4 * r + 1] * m[1] + Ph[4 * r + 2] * m[2] + Ph[4 * r + 3] * m[3] + ev[4 * s + r];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) m[r] = n[r];
+  }
+  CPMPC_GSYNC();
+  ok = __all_sync(c.gmask, ok);
+  if (!ok) return false;
+
+  // (3) forward substitution with the unit bidiagonal factor: rows 0..3 of Z and the gradient (in du[]), one
+  // right-hand side per lane, the running value carried in a register
+  for (int r = c.gl; r < 5; r += L) {
+    double* row = (r < 4) ? (Z + r * W) : du;
+    double prev = row[0];
+    for (int j = 1; j < W; ++j) {
+      prev = fma(-tl[j], prev, row[j]);
+      row[j] = prev;
+    }
+  }
+  CPMPC_GSYNC();
+
+  // (4) Gram entries G[i][j] = sum_q Z_i[q] Z_j[q] / d_q for i <= j <= 4 (j == 4: the gradient row): 14 dot products
+  // spread over the lanes, results through shuffles-free shared scratch (the first 16 slots of tl's tail are free?)
+  // -> kept in registers: every lane needs all 14, so each lane computes its share and the group exchanges them.
+  double gm[14];
+#pragma unroll
+  for (int e = 0; e < 14; ++e) gm[e] = 0.0;
+  {
+    // pair list: (0,0)(0,1)(0,2)(0,3)(1,1)(1,2)(1,3)(2,2)(2,3)(3,3)(0,4)(1,4)(2,4)(3,4)
+    // every lane accumulates over its own columns q = gl, gl + L, ...; a group sum finishes each entry
+    for (int q = c.gl; q < W; q += L) {
+      const double ti = tinv[q];
+      const double z0 = Z[q], z1 = Z[W + q], z2 = Z[2 * W + q], z3 = Z[3 * W + q], zg = du[q];
+      const double s0 = z0 * ti, s1 = z1 * ti, s2 = z2 * ti, s3 = z3 * ti;
+      gm[0] = fma(s0, z0, gm[0]);
+      gm[1] = fma(s0, z1, gm[1]);
+      gm[2] = fma(s0, z2, gm[2]);
+      gm[3] = fma(s0, z3, gm[3]);
+      gm[4] = fma(s1, z1, gm[4]);
+      gm[5] = fma(s1, z2, gm[5]);
+      gm[6] = fma(s1, z3, gm[6]);
+      gm[7] = fma(s2, z2, gm[7]);
+      gm[8] = fma(s2, z3, gm[8]);
+      gm[9] = fma(s3, z3, gm[9]);
+      gm[10] = fma(s0, zg, gm[10]);
+      gm[11] = fma(s1, zg, gm[11]);
+      gm[12] = fma(s2, zg, gm[12]);
+      gm[13] = fma(s3, zg, gm[13]);
+    }
+#pragma unroll
+    for (int e = 0; e < 14; ++e) gm[e] = group_sum<L>(gm[e], c.gmask);
+  }
+
+  // (5) 4x4 system for the row multipliers, every lane redundantly in registers
+  double A4[4][4] = {{gm[0], gm[1], gm[2], gm[3]}, {gm[1], gm[4], gm[5], gm[6]}, {gm[2], gm[5], gm[7], gm[8]},
+                     {gm[3], gm[6], gm[8], gm[9]}};
+  double sig[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double d = xs[4 * (NS - 1) + i] - target[i];
+    if (i == 1) d = mod_pi(d);
+    double invd, off;
+    if (w.wt[i] < 0.0) {
+      invd = 0.0;  // hard row
+      off = m[i] + d;
+    } else {
+      const double dd = w.wt[i] * w.wt[i];
+      if (dd > 0.0) {
+        invd = 1.0 / dd;
+        off = m[i] + d;  // (w^2 d) / w^2
+      } else {
+        invd = -1.0;  // zero weight: the row does not exist
+        off = 0.0;
+      }
+    }
+    if (invd < 0.0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        A4[i][j] = 0.0;
+        A4[j][i] = 0.0;
+      }
+      A4[i][i] = 1.0;
+      sig[i] = 0.0;
+    } else {
+      A4[i][i] += invd;
+      sig[i] = off - gm[10 + i];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    double d = A4[j][j];
+#pragma unroll
+    for (int q = 0; q < j; ++q) d -= A4[j][q] * A4[j][q];
+    if (!(d > 0.0)) ok = false;
+    const double inv = 1.0 / sqrt(d);
+    A4[j][j] = inv;
+#pragma unroll
+    for (int i = j + 1; i < 4; ++i) {
+      double sacc = A4[i][j];
+#pragma unroll
+      for (int q = 0; q < j; ++q) sacc -= A4[i][q] * A4[j][q];
+      A4[i][j] = sacc * inv;
+    }
+  }
+  if (!ok) return false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double sacc = sig[i];
+#pragma unroll
+    for (int q = 0; q < i; ++q) sacc -= A4[i][q] * sig[q];
+    sig[i] = sacc * A4[i][i];
+  }
+#pragma unroll
+  for (int i = 3; i >= 0; --i) {
+    double sacc = sig[i];
+#pragma unroll
+    for (int q = i + 1; q < 4; ++q) sacc -= A4[q][i] * sig[q];
+    sig[i] = sacc * A4[i][i];
+  }
+
+  // (6) du = -L^-T D^-1 (z_g + Z sigma); c_u . du = -(L^-1 g)^T D^-1 (z_g + Z sigma) needs no second pass over g
+  double part = 0.0;
+  for (int q = c.gl; q < W; q += L) {
+    const double zg = du[q];
+    const double wq = (zg + sig[0] * Z[q] + sig[1] * Z[W + q] + sig[2] * Z[2 * W + q] + sig[3] * Z[3 * W + q]) * tinv[q];
+    part = fma(zg, wq, part);
+    du[q] = wq;
+  }
+  cdx = -part;  // this lane's share of c_u . du
+  CPMPC_GSYNC();
+  if (c.gl == 0) {
+    double nxt = du[W - 1];
+    du[W - 1] = -nxt;
+    for (int j = W - 2; j >= 0; --j) {
+      nxt = fma(-tl[j + 1], nxt, du[j]);
+      du[j] = -nxt;
+    }
+    dxs[0] = m00;
+    dxs[1] = m01;
+    dxs[2] = m02;
+    dxs[3] = m03;
+  }
+  CPMPC_GSYNC();
+
+  // (7) node steps by forward propagation
+  double xi[4] = {m00, m01, m02, m03};
+  for (int s = 0; s < nseg; ++s) {
+    const double* Ph = Phi + 16 * s;
+    for (int a = c.gl; a < 4; a += L) {
+      double n0 = Ph[4 * a] * xi[0] + Ph[4 * a + 1] * xi[1] + ev[4 * s + a];
+      double n1 = Ph[4 * a + 2] * xi[2] + Ph[4 * a + 3] * xi[3];
+      const double* ga = Gam + a * W + s * S;
+      const double* vv = du + s * S;
+      int j = 0;
+      for (; j + 1 < S; j += 2) {
+        n0 = fma(ga[j], vv[j], n0);
+        n1 = fma(ga[j + 1], vv[j + 1], n1);
+      }
+      if (j < S) n0 = fma(ga[j], vv[j], n0);
+      dxs[4 * (s + 1) + a] = n0 + n1;
+    }
+    CPMPC_GSYNC();
+#pragma unroll
+    for (int a = 0; a < 4; ++a) xi[a] = dxs[4 * (s + 1) + a];
+  }
+  return true;
 }
 
 struct SolveResult {
@@ -557,6 +870,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
   int opt_state = OS_NOMINAL;
   double cur_f = 0.0, cur_eq = 0.0;  // Errors at the current variables
   bool have_cur = false;
+  bool tri_valid = false;  // factorisation of T (condensed QP) is cached across the iterations of one solve
   res.termination = TS_MAX_ITERATIONS;
   res.n_iter = 0;
   res.n_ls = 0;
@@ -722,7 +1036,13 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
     if (active) {
       // ---- QP step (qp.cc:679-729) -----------------------------------------------------------------------------
       double cdx = 0.0;
-      const bool qp_ok = riccati_qp<L>(c, w, lambda, x_cur, target, cdx);
+      bool qp_ok;
+      if (k.condensed && !(lambda > 0.0)) {
+        qp_ok = condensed_qp<L>(c, w, tri_valid, x_cur, target, cdx);
+      } else {
+        tri_valid = false;  // the Riccati stage matrix shares the scratch of the tridiagonal factor
+        qp_ok = riccati_qp<L>(c, w, lambda, x_cur, target, cdx);
+      }
       if (!qp_ok) {
         // QP_INDEFINITE: Solve() returns before this iteration is logged (nonlinear.cc:103-105)
         res.termination = TS_QP_INDEFINITE;
