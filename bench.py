@@ -294,17 +294,24 @@ def main():
     # ---- single-solve latency through the same boundary (batch of 1, host buffers) ------------------------------------
     lat = None
     if rank == 0:
-        one = BatchedOptimization(1, device=local_rank)
         s1, d1, p1 = states_h[:1].copy(), dyn_h[:1].copy(), sp_h[:1].copy()
-        ts = []
-        for i in range(60):
-            one.reset()
-            t0 = time.perf_counter()
-            one.step(s1, d1, p1)
-            ts.append(time.perf_counter() - t0)
-        lat = {"p50_ms": float(np.percentile(ts[10:], 50) * 1e3), "p99_ms": float(np.percentile(ts[10:], 99) * 1e3),
-               "batch": 1, "path": "cpmpc_step (host buffers)"}
-        one.close()
+
+        def batch1_latency(low_latency):
+            one = BatchedOptimization(1, device=local_rank, low_latency=low_latency)
+            ts = []
+            for i in range(60):
+                one.reset()
+                t0 = time.perf_counter()
+                one.step(s1, d1, p1)
+                ts.append(time.perf_counter() - t0)
+            one.close()
+            return float(np.percentile(ts[10:], 50) * 1e3), float(np.percentile(ts[10:], 99) * 1e3)
+
+        p50, p99 = batch1_latency(False)
+        p50_ll, p99_ll = batch1_latency(True)
+        lat = {"p50_ms": p50, "p99_ms": p99, "batch": 1, "path": "cpmpc_step (host buffers), default mapping",
+               "low_latency_flag": {"p50_ms": p50_ll, "p99_ms": p99_ll,
+                                    "note": "CPMPC_FLAG_LOW_LATENCY: two lanes per shooting segment"}}
 
     # ---- reduce over ranks: max time, summed work -----------------------------------------------------------------
     if dist is not None:

@@ -12,8 +12,10 @@ ITERLOG_STRIDE = 27
 WEIGHTS_STRIDE = 6
 
 # every symbol include/cpmpc.h declares
+FLAG_LOW_LATENCY = 1  # CPMPC_FLAG_LOW_LATENCY
+
 EXPORTED_SYMBOLS = (
-    "cpmpc_last_error", "cpmpc_version", "cpmpc_default_params", "cpmpc_create", "cpmpc_destroy", "cpmpc_batch",
+    "cpmpc_last_error", "cpmpc_version", "cpmpc_default_params", "cpmpc_create", "cpmpc_create_ex", "cpmpc_destroy", "cpmpc_batch",
     "cpmpc_solution_dim", "cpmpc_step", "cpmpc_step_device", "cpmpc_reset", "cpmpc_reset_device",
     "cpmpc_set_previous_solution",
     "cpmpc_get_previous_solution", "cpmpc_enable_iteration_log", "cpmpc_get_iteration_log", "cpmpc_sim_step_device",
@@ -89,6 +91,8 @@ def lib() -> C.CDLL:
     L.cpmpc_default_params.argtypes = [C.POINTER(CpmpcParams)]
     L.cpmpc_create.restype = C.c_int
     L.cpmpc_create.argtypes = [C.POINTER(CpmpcParams), C.c_int64, C.c_int, C.POINTER(vp)]
+    L.cpmpc_create_ex.restype = C.c_int
+    L.cpmpc_create_ex.argtypes = [C.POINTER(CpmpcParams), C.c_int64, C.c_int, C.c_uint32, C.POINTER(vp)]
     L.cpmpc_destroy.restype = C.c_int
     L.cpmpc_destroy.argtypes = [vp]
     L.cpmpc_batch.restype = C.c_int64

@@ -63,13 +63,16 @@ class BatchedOptimization:
     `reset` == Reset, `set_previous_solution` == SetPreviousSolution; the warm start lives on the device.
     """
 
-    def __init__(self, batch: int, params: Optional[_capi.CpmpcParams] = None, device: int = 0, **overrides):
+    def __init__(self, batch: int, params: Optional[_capi.CpmpcParams] = None, device: int = 0,
+                 low_latency: bool = False, **overrides):
         self._h = C.c_void_p()
         self._lib = _capi.lib()
         self.params = params if params is not None else make_params(**overrides)
         if params is not None and overrides:
             raise ValueError("pass either params or keyword overrides")
-        _capi.check(self._lib.cpmpc_create(C.byref(self.params), int(batch), int(device), C.byref(self._h)))
+        flags = _capi.FLAG_LOW_LATENCY if low_latency else 0
+        _capi.check(self._lib.cpmpc_create_ex(C.byref(self.params), int(batch), int(device), flags,
+                                              C.byref(self._h)))
         self.batch = int(batch)
         self.device = int(device)
         self.W = int(self.params.window_length)

@@ -180,6 +180,10 @@ void cpmpc_default_params(cpmpc_params* p) {
 }
 
 int cpmpc_create(const cpmpc_params* params, int64_t batch, int device, cpmpc_handle* out) {
+  return cpmpc_create_ex(params, batch, device, 0u, out);
+}
+
+int cpmpc_create_ex(const cpmpc_params* params, int64_t batch, int device, uint32_t flags, cpmpc_handle* out) {
   if (params == nullptr || out == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "null argument");
   *out = nullptr;
   // preconditions of Optimization::Optimization (optimization.cc:13-22) and CheckParams (nonlinear.cc:49-73)
@@ -252,18 +256,17 @@ int cpmpc_create(const cpmpc_params* params, int64_t batch, int device, cpmpc_ha
   int base_lanes = Pow2Ceil(k.nseg);
   if (base_lanes > 32) base_lanes = 32;
   int lanes = base_lanes;
-  if (2 * base_lanes <= 32 && k.S >= 2 && (2 * base_lanes) / k.nseg >= 2) lanes = 2 * base_lanes;
+  // CPMPC_FLAG_LOW_LATENCY: two lanes per segment.  It shortens one solve's dependent chain (batch-1 latency
+  // 0.73 -> 0.60 ms at the defaults) but leaves half of every warp idle during the merit rollouts: 3.88 M solves/s
+  // instead of 4.28 M at B = 4096, 3.6 M instead of 5.3 M at B = 65536 (profiles/r01_lane_sweep.jsonl).  It is
+  // opt-in rather than picked from the batch size because the chunked linearisation rounds differently, and results
+  // must not depend on how a caller happens to group instances into batches.
+  if ((flags & CPMPC_FLAG_LOW_LATENCY) != 0u && 2 * base_lanes <= 32 && k.S >= 2 && (2 * base_lanes) / k.nseg >= 2) {
+    lanes = 2 * base_lanes;
+  }
   if (const char* env = std::getenv("CPMPC_LANES")) {
     const int v = std::atoi(env);
     if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) lanes = v;
-  }
-  h->lanes = lanes;
-  k.cps = lanes / k.nseg;
-  if (k.cps < 1) k.cps = 1;
-  if (k.cps > k.S) k.cps = k.S;
-  if (const char* env = std::getenv("CPMPC_CHUNKS")) {
-    const int v = std::atoi(env);
-    if (v >= 1 && v <= k.S && v * k.nseg <= lanes) k.cps = v;
   }
   // QP method for the undamped iterations: condensed while the horizon is short enough for open-loop sensitivity
   // products to stay accurate, Riccati beyond (and always for Levenberg-Marquardt iterations)
@@ -272,12 +275,27 @@ int cpmpc_create(const cpmpc_params* params, int64_t batch, int device, cpmpc_ha
     if (std::strcmp(env, "riccati") == 0) k.condensed = 0;
     if (std::strcmp(env, "condensed") == 0) k.condensed = 1;
   }
-  BuildLayout(k);
-  const int groups_per_warp = 32 / lanes;
-  const size_t smem_per_warp = sizeof(double) * static_cast<size_t>(k.stride) * groups_per_warp;
-
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  const bool chunked = lanes > base_lanes;
+  size_t smem_per_warp = 0;
+  for (;;) {
+    // chunks per segment: only the low-latency mapping splits segments; lanes added below to fit shared memory
+    // (long single-shooting segments need a large Riccati stage matrix per instance) just widen the QP loops
+    k.cps = chunked ? (2 * base_lanes) / k.nseg : 1;
+    if (k.cps < 1) k.cps = 1;
+    if (k.cps > k.S) k.cps = k.S;
+    if (const char* env = std::getenv("CPMPC_CHUNKS")) {
+      const int v = std::atoi(env);
+      if (v >= 1 && v <= k.S && v * k.nseg <= lanes) k.cps = v;
+    }
+    BuildLayout(k);
+    smem_per_warp = sizeof(double) * static_cast<size_t>(k.stride) * (32 / lanes);
+    if (smem_per_warp <= static_cast<size_t>(prop.sharedMemPerBlockOptin) || lanes == 32) break;
+    lanes *= 2;
+  }
+  h->lanes = lanes;
+  const int groups_per_warp = 32 / lanes;
   if (smem_per_warp > static_cast<size_t>(prop.sharedMemPerBlockOptin)) {
     delete h;
     return Fail(CPMPC_ERR_UNSUPPORTED, "problem needs " + std::to_string(smem_per_warp) +

@@ -93,6 +93,15 @@ void cpmpc_default_params(cpmpc_params* params);
 /* Replaces `Optimization::Optimization(const OptimizationParams&)` (optimization.cc:13-22) for `batch` independent
  * controllers on CUDA device `device`.  Validates the same preconditions. */
 int cpmpc_create(const cpmpc_params* params, int64_t batch, int device, cpmpc_handle* out);
+/* Same with option flags.  The default mapping (flags == 0) gives results that do not depend on how instances are
+ * grouped into batches: instance i alone and instance i inside any batch produce the same bits.
+ *   CPMPC_FLAG_LOW_LATENCY  two lanes per shooting segment: the linearisation of a segment runs as two half-length
+ *                           chunks side by side.  Shortens one solve's dependent chain (0.73 -> 0.60 ms for a batch
+ *                           of one at the defaults) at the price of throughput on large batches, and rounds the
+ *                           segment Jacobian products differently (parity with the reference is unchanged, bitwise
+ *                           equality with the default mapping is not kept). */
+#define CPMPC_FLAG_LOW_LATENCY 1u
+int cpmpc_create_ex(const cpmpc_params* params, int64_t batch, int device, uint32_t flags, cpmpc_handle* out);
 int cpmpc_destroy(cpmpc_handle h);
 
 /* Problem dimensions derived from the params of a handle. */

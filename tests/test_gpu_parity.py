@@ -328,6 +328,20 @@ def test_full_size_properties():
     assert np.array_equal(single.u, out.u[idx])
 
 
+def test_low_latency_mapping_matches_oracle(oracle):
+    """CPMPC_FLAG_LOW_LATENCY (two lanes per shooting segment, chunked linearisation) against the oracle: same parity
+    bar as the default mapping; it is NOT required to be bitwise equal to the default mapping."""
+    from cart_pole_mpc_b200 import BatchedOptimization, synthetic
+    for over in (dict(), dict(state_spacing=5, max_iterations=10)):
+        B = 512
+        st, dy, sp = synthetic.swingup_batch(B, seed=11)
+        ora = oracle.batch_step(oracle.opt_array(**over), st, dy, sp, want_iter_log=False)
+        out = BatchedOptimization(B, low_latency=True, **over).step(st, dy, sp)
+        rel = np.abs(out.merit - ora.merit) / np.maximum(np.abs(ora.merit), 1e-300)
+        assert (rel <= REL_COST_TOL).mean() >= 0.95
+        assert (out.stats["n_iterations"] == ora.n_iterations).mean() >= 0.98
+
+
 def test_sharding_two_handles_equal_one(oracle):
     """Multi-GPU data path in miniature: two handles over the two halves == one handle over the whole batch."""
     from cart_pole_mpc_b200 import synthetic
