@@ -167,6 +167,223 @@ def run_reference(args):
     return 0
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# Secondary workloads (BASELINE.json configs[2] and configs[3]); the default bench line stays configs[1].
+# ----------------------------------------------------------------------------------------------------------------------
+def _dist_setup():
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    return world, rank, local_rank, dist, torch.device("cuda", local_rank)
+
+
+def _max_over_ranks(dist, dev, values):
+    import torch
+    if dist is None:
+        return values
+    t = torch.tensor(values, dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def _sum_over_ranks(dist, dev, values):
+    import torch
+    if dist is None:
+        return values
+    t = torch.tensor(values, dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [float(v) for v in t]
+
+
+def run_closed_loop(args):
+    """configs[2]: receding-horizon MPC, B plants x n control steps, warm-started solves, plant integrated on the
+    device between solves (one launch for the whole loop).  A "step" of the bench = the whole closed loop."""
+    import torch
+    from cart_pole_mpc_b200 import BatchedOptimization, measure_fp64_peak, launch_count, synthetic
+    world, rank, local_rank, dist, dev = _dist_setup()
+    B = args.batch if args.batch != DEFAULT_BATCH else 65536
+    T = args.cl_steps
+    over = dict(state_spacing=5, max_iterations=10) if args.test_variant else {}
+    S = over.get("state_spacing", 10)
+    st_h, dy_h, sp_h = synthetic.swingup_batch(B, seed=synthetic.SEED_CONFIG2 + 1, first=rank * B)
+    solver = BatchedOptimization(B, device=local_rank, **over)
+    dy_d, sp_d = torch.from_numpy(dy_h).to(dev), torch.from_numpy(sp_h).to(dev)
+    st0_d = torch.from_numpy(st_h).to(dev)
+    st_d = st0_d.clone()
+    counts_d = torch.zeros(4, dtype=torch.int64, device=dev)
+
+    def one_step():
+        st_d.copy_(st0_d)
+        counts_d.zero_()
+        solver.reset_device()
+        solver.closed_loop_device(T, st_d, dy_d, sp_d, stats_sum=counts_d)
+
+    steps = max(1, min(args.steps, 5))
+    for _ in range(1 if args.warmup < 1 else min(args.warmup, 2)):
+        one_step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one_step()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    total_ms = e0.elapsed_time(e1)
+    launches = launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    counts = counts_d.cpu().numpy().astype(np.float64)
+    f_roll = 40 * (4 * 76 + 60)  # SURVEY.md 8(d): initial-guess fill and predicted states, once each per solve
+    flops = float(algorithmic_flops(counts[1], counts[2], S=S) + (counts[0] - 1) * 2 * f_roll)
+    # e2e: host buffers in, final states + applied controls out
+    torch.cuda.synchronize()
+    solver.reset()  # cold first tick, like a freshly constructed Optimization
+    t0 = time.perf_counter()
+    fin, ctl, cnt = solver.closed_loop(T, st_h, dy_h, sp_h)
+    e2e_s = time.perf_counter() - t0
+    (total_ms, e2e_s) = _max_over_ranks(dist, dev, [total_ms, e2e_s])
+    (solves_all, flops_all) = _sum_over_ranks(dist, dev, [counts[0], flops])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+    peak = measure_fp64_peak(local_rank)
+    per_loop_ms = total_ms / steps
+    line = {
+        "metric": "batched MPC solves/sec (FP64), closed-loop receding horizon, warm-started", "value": solves_all / (per_loop_ms * 1e-3),
+        "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": per_loop_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"closed loop: {B} plants per GPU x {T} control steps, Step + Simulator::Step(1 ms RK4 "
+                               f"sub-steps) per tick, W=40 S={S} (BASELINE.json configs[2])", "batch_per_gpu": B,
+                   "control_steps": T, "l2": "state + warm start working set 65536 x 0.6 KB streams through L2 every tick"},
+        "e2e": {"value": world * B * T / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * 14 * 8,
+                "d2h_bytes_per_step": B * (4 + T) * 8, "path": "cpmpc_closed_loop: host buffers -> one launch -> D2H"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "fp64", "achieved": flops / (per_loop_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                     "frac": flops / (per_loop_ms * 1e-3) / 1e12 / peak, "traffic": None,
+                     "flops_model": "SURVEY.md 8(d) from the solver's summed n_iter / n_ls counters"},
+        "mean_sqp_iterations": counts[1] / counts[0], "mean_merit_evaluations": counts[2] / counts[0],
+        "bad_terminations": int(counts[3]),
+    }
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import oracle_py
+        nb, nt = 256, min(T, 100)
+        t0 = time.perf_counter()
+        _, ctl_o, _, cnt_o, _, thr = oracle_py.closed_loop(oracle_py.opt_array(**over), st_h[:nb], dy_h[:nb], sp_h[:nb], nt)
+        dt_cpu = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": nb * nt / dt_cpu, "unit": UNIT, "cores": int(thr), "kind": "port",
+                                "sample": f"the first {nb} plants x {nt} control steps, one plant per thread"}
+        # closed-loop parity on the sample: applied controls of the first ticks (before chaos separates trajectories)
+        d = np.abs(ctl[:nb, :nt] - ctl_o)
+        line["cpu_baseline"]["bad_terminations_in_sample"] = int(cnt_o[3])
+        line["parity"] = {"median_abs_du_first_tick": float(np.median(d[:, 0])),
+                          "frac_plants_all_ticks_within_1e-6": float((d.max(axis=1) <= 1e-6).mean()),
+                          "frac_ticks_within_1e-8": float((d <= 1e-8).mean())}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_sweep(args):
+    """configs[3]: parameter / cost-weight sweep with a 4x horizon (W=160, S=10), 1M instances over 8 GPUs
+    = 131072 per GPU, cold start."""
+    import torch
+    from cart_pole_mpc_b200 import BatchedOptimization, measure_fp64_peak, launch_count, synthetic, _capi
+    world, rank, local_rank, dist, dev = _dist_setup()
+    B = args.batch if args.batch != DEFAULT_BATCH else 131072
+    W, S = 160, 10
+    st_h, dy_h, sp_h, wt_h = synthetic.sweep_batch(B, first=rank * B)
+    solver = BatchedOptimization(B, device=local_rank, window_length=W, state_spacing=S)
+    to = lambda a: torch.from_numpy(a).to(dev)
+    st_d, dy_d, sp_d, wt_d = to(st_h), to(dy_h), to(sp_h), to(wt_h)
+    u_d = torch.empty((B, W), dtype=torch.float64, device=dev)
+    stats_d = torch.empty((B, 56), dtype=torch.uint8, device=dev)
+
+    def one_step():
+        solver.reset_device()
+        solver.step_device(st_d, dy_d, sp_d, u_d, weights=wt_d, stats_out=stats_d)
+
+    steps = max(1, min(args.steps, 5))
+    for _ in range(1):
+        one_step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one_step()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    total_ms = e0.elapsed_time(e1)
+    launches = launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    stats = np.frombuffer(stats_d.cpu().numpy().tobytes(), dtype=_capi.STATS_DTYPE)
+    flops = float(algorithmic_flops(stats["n_iterations"].astype(np.float64), stats["n_line_search_steps"].astype(np.float64),
+                                    W=W, S=S, n_cost=1 + 2 * W).sum())
+    (total_ms,) = _max_over_ranks(dist, dev, [total_ms])
+    (flops_all,) = _sum_over_ranks(dist, dev, [flops])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+    peak = measure_fp64_peak(local_rank)
+    ms = total_ms / steps
+    hist = np.bincount(np.maximum(stats["termination_state"], 0), minlength=7).tolist()
+    line = {
+        "metric": "batched MPC solves/sec (FP64), long-horizon parameter/cost-weight sweep, cold start", "value": world * B / (ms * 1e-3),
+        "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": 1, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{B}-instance sweep per GPU (1M over 8 GPUs), W=160 S=10 max_iter=8, per-instance dynamics "
+                               "parameters, cost weights and set points (BASELINE.json configs[3])", "batch_per_gpu": B,
+                   "qp": "segment-wise Riccati (16 stages)", "l2": "inputs 10 MB + results 170 MB per step exceed L2"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "fp64", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                     "frac": flops / (ms * 1e-3) / 1e12 / peak, "traffic": None,
+                     "flops_model": "SURVEY.md 8(d) with W=160 (F_qp canonical = W^3/3 + ...)"},
+        "mean_sqp_iterations": float(stats["n_iterations"].mean()),
+        "mean_merit_evaluations": float(stats["n_line_search_steps"].mean()), "termination_hist": hist,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import oracle_py
+        nb = 512
+        t0 = time.perf_counter()
+        ora = oracle_py.batch_step(oracle_py.opt_array(window_length=W, state_spacing=S), st_h[:nb], dy_h[:nb], sp_h[:nb],
+                                   weights=wt_h[:nb], want_iter_log=False)
+        dt_cpu = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": nb / dt_cpu, "unit": UNIT, "cores": int(ora.threads), "kind": "port",
+                                "sample": f"the first {nb} instances, one instance per thread"}
+        g = stats["f"][:nb] + stats["penalty"][:nb] * stats["equality"][:nb]
+        rel = np.abs(g - ora.merit) / np.maximum(np.abs(ora.merit), 1e-300)
+        line["parity"] = {"frac_within_1e-8_rel_cost": float((rel <= 1e-8).mean()),
+                          "iteration_count_match": float((stats["n_iterations"][:nb] == ora.n_iterations).mean()),
+                          "termination_match": float((stats["termination_state"][:nb] == ora.termination).mean())}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -177,7 +394,15 @@ def main():
     ap.add_argument("--allgather", action="store_true",
                     help="also all-gather u and stats across ranks inside the timed region (NCCL)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4"],
+                    help="config2: the headline bench (default); config3: closed loop; config4: long-horizon sweep")
+    ap.add_argument("--cl-steps", type=int, default=500, help="control steps of the closed loop (config3)")
+    ap.add_argument("--test-variant", action="store_true", help="config3 with optimization_test.cc's S=5, max_iter=10")
     args = ap.parse_args()
+    if args.impl != "reference" and args.workload == "config3":
+        return run_closed_loop(args)
+    if args.impl != "reference" and args.workload == "config4":
+        return run_sweep(args)
 
     if args.impl == "reference":
         if args.steps > 20:
