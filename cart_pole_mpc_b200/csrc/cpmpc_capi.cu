@@ -119,6 +119,7 @@ void BuildLayout(KernelCfg& k) {
   k.off_aug = take(n_ric > n_cond ? n_ric : n_cond);
   k.off_vbuf = take(25 + XI_DIM * NR_MAX);
   k.off_invd = take(S);
+  k.off_dyn = take(12);
   // odd stride (in doubles) so that the same field of neighbouring instances falls into different banks
   k.stride = off | 1;
   k.kk_stride = nseg * NCOL_MAX * S;

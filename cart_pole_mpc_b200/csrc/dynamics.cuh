@@ -57,6 +57,36 @@ __device__ __forceinline__ DynConst make_dyn_const(const double* __restrict__ p)
   return c;
 }
 
+// DynConst parked in / fetched from shared memory (12 doubles).
+__device__ __forceinline__ void store_dyn_const(double* dst, const DynConst& c) {
+  dst[0] = c.m1;
+  dst[1] = c.m_total;
+  dst[2] = c.len;
+  dst[3] = c.inv_len;
+  dst[4] = c.len2;
+  dst[5] = c.m_over_l2;
+  dst[6] = c.drag_k;
+  dst[7] = c.fric_k;
+  dst[8] = c.inv_v_cut;
+  dst[9] = c.k_s;
+  dst[10] = c.x_s;
+  dst[11] = c.grav;
+}
+__device__ __forceinline__ void load_dyn_const(DynConst& c, const double* src) {
+  c.m1 = src[0];
+  c.m_total = src[1];
+  c.len = src[2];
+  c.inv_len = src[3];
+  c.len2 = src[4];
+  c.m_over_l2 = src[5];
+  c.drag_k = src[6];
+  c.fric_k = src[7];
+  c.inv_v_cut = src[8];
+  c.k_s = src[9];
+  c.x_s = src[10];
+  c.grav = src[11];
+}
+
 // Map an angle to (-pi, pi].  fmod(a, 2pi) == a exactly whenever |a| < 2pi, which skips CUDA's software fmod on
 // the overwhelmingly common path.
 __device__ __forceinline__ double mod_pi(double a) {

@@ -29,6 +29,58 @@
 namespace cpmpc {
 namespace fm {
 
+// Polynomial / range-reduction constants.  On the device they live in constant memory: sm_100a has no 64-bit
+// immediates, so a literal costs two UMOVs (and a uniform-datapath latency) in front of every DFMA that uses it,
+// whereas a constant-bank table is fetched into uniform registers two doubles per LDCU.128.
+#define CPMPC_FM_CONSTS(X) \
+  X(two_over_pi, 0.63661977236758138) \
+  X(magic, 6755399441055744.0) \
+  X(pio2_1, 1.5707963267948966) \
+  X(pio2_2, 6.123233995736766e-17) \
+  X(pio2_3, -1.4973849048591698e-33) \
+  X(s6, 1.58969099521155010221e-10) \
+  X(s5, -2.50507602534068634195e-08) \
+  X(s4, 2.75573137070700676789e-06) \
+  X(s3, -1.98412698298579493134e-04) \
+  X(s2, 8.33333333332248946124e-03) \
+  X(s1, -1.66666666666666324348e-01) \
+  X(c6, -1.13596475577881948265e-11) \
+  X(c5, 2.08757232129817482790e-09) \
+  X(c4, -2.75573143513906633035e-07) \
+  X(c3, 2.48015872894767294178e-05) \
+  X(c2, -1.38888888888741095749e-03) \
+  X(c1, 4.16666666666666019037e-02) \
+  X(log2e, 1.4426950408889634) \
+  X(ln2_hi, 6.93147180369123816490e-01) \
+  X(ln2_lo, 1.90821492927058770002e-10) \
+  X(e12, 1.0 / 479001600.0) \
+  X(e10, 1.0 / 3628800.0) \
+  X(e8, 1.0 / 40320.0) \
+  X(e6, 1.0 / 720.0) \
+  X(e4, 1.0 / 24.0) \
+  X(e13, 1.0 / 6227020800.0) \
+  X(e11, 1.0 / 39916800.0) \
+  X(e9, 1.0 / 362880.0) \
+  X(e7, 1.0 / 5040.0) \
+  X(e5, 1.0 / 120.0) \
+  X(e3, 1.0 / 6.0)
+struct FmConsts {
+#define CPMPC_X(name, value) double name;
+  CPMPC_FM_CONSTS(CPMPC_X)
+#undef CPMPC_X
+};
+#define CPMPC_X(name, value) value,
+#if defined(__CUDACC__)
+__constant__ FmConsts kc_dev = {CPMPC_FM_CONSTS(CPMPC_X)};
+#endif
+static const FmConsts kc_host = {CPMPC_FM_CONSTS(CPMPC_X)};
+#undef CPMPC_X
+#if defined(__CUDA_ARCH__)
+#define CPMPC_K(name) (::cpmpc::fm::kc_dev.name)
+#else
+#define CPMPC_K(name) (::cpmpc::fm::kc_host.name)
+#endif
+
 CPMPC_HD double rcp_seed(double x) {
 #if defined(__CUDA_ARCH__)
   double y;
@@ -77,8 +129,8 @@ CPMPC_HD void sqrt_rsqrt(double x, double& root, double& inv_root) {
 // sin and cos for |x| < 2^20 (the pole angle stays within a few turns between two mod_pi wraps).
 CPMPC_HD void sincos_bf(double x, double& s_out, double& c_out) {
   // k = round(x * 2/pi) with the 1.5 * 2^52 trick; its low bits give the quadrant
-  const double magic = 6755399441055744.0;
-  const double t = CPMPC_FMA(x, 0.63661977236758138, magic);
+  const double magic = CPMPC_K(magic);
+  const double t = CPMPC_FMA(x, CPMPC_K(two_over_pi), magic);
   const double kd = t - magic;
   int64_t tb;
 #if defined(__CUDA_ARCH__)
@@ -88,22 +140,22 @@ CPMPC_HD void sincos_bf(double x, double& s_out, double& c_out) {
 #endif
   const int q = (int)(tb & 3);
   // Cody-Waite with a three-part pi/2 (the FMAs keep the products exact)
-  double r = CPMPC_FMA(-kd, 1.5707963267948966, x);
-  r = CPMPC_FMA(-kd, 6.123233995736766e-17, r);
-  r = CPMPC_FMA(-kd, -1.4973849048591698e-33, r);
+  double r = CPMPC_FMA(-kd, CPMPC_K(pio2_1), x);
+  r = CPMPC_FMA(-kd, CPMPC_K(pio2_2), r);
+  r = CPMPC_FMA(-kd, CPMPC_K(pio2_3), r);
   const double z = r * r;
   // fdlibm kernel polynomials on |r| <= pi/4
-  double ps = CPMPC_FMA(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-  ps = CPMPC_FMA(z, ps, 2.75573137070700676789e-06);
-  ps = CPMPC_FMA(z, ps, -1.98412698298579493134e-04);
-  ps = CPMPC_FMA(z, ps, 8.33333333332248946124e-03);
-  ps = CPMPC_FMA(z, ps, -1.66666666666666324348e-01);
+  double ps = CPMPC_FMA(z, CPMPC_K(s6), CPMPC_K(s5));
+  ps = CPMPC_FMA(z, ps, CPMPC_K(s4));
+  ps = CPMPC_FMA(z, ps, CPMPC_K(s3));
+  ps = CPMPC_FMA(z, ps, CPMPC_K(s2));
+  ps = CPMPC_FMA(z, ps, CPMPC_K(s1));
   const double sn = CPMPC_FMA(z * r, ps, r);
-  double pc = CPMPC_FMA(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-  pc = CPMPC_FMA(z, pc, -2.75573143513906633035e-07);
-  pc = CPMPC_FMA(z, pc, 2.48015872894767294178e-05);
-  pc = CPMPC_FMA(z, pc, -1.38888888888741095749e-03);
-  pc = CPMPC_FMA(z, pc, 4.16666666666666019037e-02);
+  double pc = CPMPC_FMA(z, CPMPC_K(c6), CPMPC_K(c5));
+  pc = CPMPC_FMA(z, pc, CPMPC_K(c4));
+  pc = CPMPC_FMA(z, pc, CPMPC_K(c3));
+  pc = CPMPC_FMA(z, pc, CPMPC_K(c2));
+  pc = CPMPC_FMA(z, pc, CPMPC_K(c1));
   const double zz = z * z;
   const double cs = CPMPC_FMA(zz, pc, CPMPC_FMA(-0.5, z, 1.0));
   const bool swap = (q & 1) != 0;
@@ -117,8 +169,8 @@ CPMPC_HD void sincos_bf(double x, double& s_out, double& c_out) {
 CPMPC_HD double tanh_bf(double x) {
   const double ax = fmin(fabs(x), 20.0);
   const double y = -2.0 * ax;  // em = exp(y) in (4e-18, 1]
-  const double magic = 6755399441055744.0;
-  const double t = CPMPC_FMA(y, 1.4426950408889634, magic);
+  const double magic = CPMPC_K(magic);
+  const double t = CPMPC_FMA(y, CPMPC_K(log2e), magic);
   const double nd = t - magic;
   int64_t tb;
 #if defined(__CUDA_ARCH__)
@@ -127,21 +179,21 @@ CPMPC_HD double tanh_bf(double x) {
   memcpy(&tb, &t, sizeof(tb));
 #endif
   const int n = (int)(int32_t)(tb & 0xffffffff);  // in [-58, 0]
-  double r = CPMPC_FMA(-nd, 6.93147180369123816490e-01, y);
-  r = CPMPC_FMA(-nd, 1.90821492927058770002e-10, r);
+  double r = CPMPC_FMA(-nd, CPMPC_K(ln2_hi), y);
+  r = CPMPC_FMA(-nd, CPMPC_K(ln2_lo), r);
   // exp(r), |r| <= ln2/2: Taylor to r^13, even/odd split to halve the dependent depth
   const double r2 = r * r;
-  double pe = CPMPC_FMA(r2, 1.0 / 479001600.0, 1.0 / 3628800.0);  // r^12, r^10
-  pe = CPMPC_FMA(r2, pe, 1.0 / 40320.0);
-  pe = CPMPC_FMA(r2, pe, 1.0 / 720.0);
-  pe = CPMPC_FMA(r2, pe, 1.0 / 24.0);
+  double pe = CPMPC_FMA(r2, CPMPC_K(e12), CPMPC_K(e10));  // r^12, r^10
+  pe = CPMPC_FMA(r2, pe, CPMPC_K(e8));
+  pe = CPMPC_FMA(r2, pe, CPMPC_K(e6));
+  pe = CPMPC_FMA(r2, pe, CPMPC_K(e4));
   pe = CPMPC_FMA(r2, pe, 0.5);
   pe = CPMPC_FMA(r2, pe, 1.0);
-  double po = CPMPC_FMA(r2, 1.0 / 6227020800.0, 1.0 / 39916800.0);  // r^13, r^11
-  po = CPMPC_FMA(r2, po, 1.0 / 362880.0);
-  po = CPMPC_FMA(r2, po, 1.0 / 5040.0);
-  po = CPMPC_FMA(r2, po, 1.0 / 120.0);
-  po = CPMPC_FMA(r2, po, 1.0 / 6.0);
+  double po = CPMPC_FMA(r2, CPMPC_K(e13), CPMPC_K(e11));  // r^13, r^11
+  po = CPMPC_FMA(r2, po, CPMPC_K(e9));
+  po = CPMPC_FMA(r2, po, CPMPC_K(e7));
+  po = CPMPC_FMA(r2, po, CPMPC_K(e5));
+  po = CPMPC_FMA(r2, po, CPMPC_K(e3));
   po = CPMPC_FMA(r2, po, 1.0);
   const double er = CPMPC_FMA(r, po, pe);
   // scale by 2^n (n in [-58, 0]: always a normal number)

@@ -44,6 +44,7 @@ struct KernelCfg {
   int nchunk;  // nseg * cps
   int stride;  // doubles of shared memory per instance
   int off_xs, off_u, off_dxs, off_du, off_phi, off_e, off_gam, off_xk, off_phic, off_aug, off_vbuf, off_invd;
+  int off_dyn;  // this instance's DynConst (12 doubles): phase functions reload it instead of pinning registers
   int off_xc, off_uc, off_xkc;  // line-search candidates: alias the Gamma block (dead after the QP)
   int kk_stride;                // doubles of global scratch per group: nseg * NCOL_MAX * S Riccati gains
   double dt, rel_tol, first_tol, abs_tol, pen_init, pen_scale, rho, armijo_c1;
@@ -106,6 +107,9 @@ struct Ctx {
 };
 
 #define CPMPC_GSYNC() __syncwarp(c.gmask)
+// Compiler-level fence around the hot rollout loops: everything whose address has escaped (the cold solver scalars
+// below) is written back to local memory before and re-read after, so it does not occupy registers inside.
+#define CPMPC_PARK() asm volatile("" ::: "memory")
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Cost terms over the controls (optimization.cc:270-301): 0.5 * sum of squared residuals for the columns owned by
@@ -174,15 +178,20 @@ __device__ __forceinline__ void boundary_terms(const KernelCfg& k, const Weights
 // Each lane integrates its own segments without Jacobians; the defects against the next shooting state are L1-summed.
 // The states at the chunk boundaries inside a segment are left in `xk_out` for the next linearisation.
 // ---------------------------------------------------------------------------------------------------------------------
+// The rollouts of one merit evaluation for this lane's segments, as a real (not inlined) function: inside the solver
+// loop some 230 registers are live across the call site and ptxas schedules an inlined copy of the dynamics with 11
+// double temporaries, i.e. its four dependent chains strictly one after the other.  Behind a call boundary the body
+// gets the whole register file (the caller's live values are saved around the call: a few hundred cycles per
+// 10-step rollout).  Returns this lane's share of the L1 norm of the shooting defects.
 template <int L>
-__device__ __forceinline__ void evaluate_errors(const Ctx& c, const DynConst& P, const Weights& w, const double* xx,
-                                                const double* uu, double* xk_out, const double x_cur[4],
-                                                const double set_point, const double u_prev, double& f_out,
-                                                double& eq_out) {
-  const KernelCfg& k = *c.cfg;
-  const int S = k.S, cps = k.cps;
+__device__ __forceinline__ double rollout_defects(const double* __restrict__ dynp, const double* __restrict__ xx,
+                                               const double* __restrict__ uu, double* __restrict__ xk_out,
+                                               const int gl, const int nseg, const int S, const int cps,
+                                               const double dt) {
+  DynConst P;
+  load_dyn_const(P, dynp);
   double eq = 0.0;
-  for (int s = c.gl; s < k.nseg; s += L) {
+  for (int s = gl; s < nseg; s += L) {
     double x[4] = {xx[4 * s], xx[4 * s + 1], xx[4 * s + 2], xx[4 * s + 3]};
     int cc = 1;
     int nb = (cps > 1) ? (S / cps) : S;  // first step of chunk cc
@@ -196,7 +205,7 @@ __device__ __forceinline__ void evaluate_errors(const Ctx& c, const DynConst& P,
         ++cc;
         nb = (cc < cps) ? (cc * S) / cps : S;
       }
-      rk4_step<false>(P, x, uu[s * S + i], k.dt);
+      rk4_step<false>(P, x, uu[s * S + i], dt);
     }
     x[1] = mod_pi(x[1]);
     const double* xn = xx + 4 * (s + 1);
@@ -205,6 +214,16 @@ __device__ __forceinline__ void evaluate_errors(const Ctx& c, const DynConst& P,
     eq += fabs(x[2] - xn[2]);
     eq += fabs(x[3] - xn[3]);
   }
+  return eq;
+}
+
+template <int L>
+__device__ __forceinline__ void evaluate_errors(const Ctx& c, const Weights& w, const double* xx,
+                                                const double* uu, double* xk_out, const double x_cur[4],
+                                                const double set_point, const double u_prev, double& f_out,
+                                                double& eq_out) {
+  const KernelCfg& k = *c.cfg;
+  double eq = rollout_defects<L>(c.sm + k.off_dyn, xx, uu, xk_out, c.gl, k.nseg, k.S, k.cps, k.dt);
   double f = control_cost_partial<L>(c, w, uu, u_prev);
   if (c.gl == 0) {
     double ft, eb;
@@ -844,8 +863,8 @@ struct SolveResult {
 // exit xs/u hold the solution.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int L>
-__device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, const DynConst& P, const Weights& w,
-                                            const double x_cur[4], const double set_point, const double u_prev,
+__device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, const Weights& w,
+                                            const double x_cur[4], const double& set_point, const double& u_prev,
                                             double* iter_log, SolveResult& res) {
   const KernelCfg& k = *c.cfg;
   double* xs = c.sm + k.off_xs;
@@ -864,13 +883,32 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
   const double target[4] = {set_point, half_pi, 0.0, 0.0};
   const int W = k.W, S = k.S, NS = k.NS, nseg = k.nseg, cps = k.cps;
 
-  bool active = active_in;
-  double lambda = 0.0;  // params.lambda_initial (nonlinear.hpp:104)
-  double penalty = k.pen_init;
-  int opt_state = OS_NOMINAL;
-  double cur_f = 0.0, cur_eq = 0.0;  // Errors at the current variables
-  bool have_cur = false;
-  bool tri_valid = false;  // factorisation of T (condensed QP) is cached across the iterations of one solve
+  // Cold solver scalars: kept in a struct whose address escapes, so that CPMPC_PARK() moves them out of the
+  // register file for the duration of the rollout loops (see CPMPC_PARK).
+  struct Cold {
+    double lambda, penalty, cur_f, cur_eq;
+    double f0, eq0, d_f, d_eq, lambda_in;
+    double alpha, a_prev, phi_prev, a_prev2, phi_prev2, step_f, step_eq, phi0, dphi0, linf;
+    int opt_state, step_result, n_steps;
+    bool active, have_cur, tri_valid, ls_done;
+  } cold;
+  asm volatile("" : : "l"(&cold) : "memory");
+  bool& active = cold.active;
+  double& lambda = cold.lambda;
+  double& penalty = cold.penalty;
+  int& opt_state = cold.opt_state;
+  double& cur_f = cold.cur_f;
+  double& cur_eq = cold.cur_eq;
+  bool& have_cur = cold.have_cur;
+  bool& tri_valid = cold.tri_valid;
+  active = active_in;
+  lambda = 0.0;  // params.lambda_initial (nonlinear.hpp:104)
+  penalty = k.pen_init;
+  opt_state = OS_NOMINAL;
+  cur_f = 0.0;
+  cur_eq = 0.0;  // Errors at the current variables
+  have_cur = false;
+  tri_valid = false;  // factorisation of T (condensed QP) is cached across the iterations of one solve
   res.termination = TS_MAX_ITERATIONS;
   res.n_iter = 0;
   res.n_ls = 0;
@@ -880,12 +918,23 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
   for (int iter = 0; iter < k.max_iter; ++iter) {
     if (!__any_sync(0xffffffffu, active)) break;
 
-    double f0 = 0.0, eq0 = 0.0, d_f = 0.0, d_eq = 0.0;
-    const double lambda_in = lambda;
+    double& f0 = cold.f0;
+    double& eq0 = cold.eq0;
+    double& d_f = cold.d_f;
+    double& d_eq = cold.d_eq;
+    double& lambda_in = cold.lambda_in;
+    f0 = 0.0;
+    eq0 = 0.0;
+    d_f = 0.0;
+    d_eq = 0.0;
+    lambda_in = lambda;
 
     if (active) {
       // ---- linearise: one chunk of consecutive knots per lane, RK4 with the Jacobian chain in forward mode -------
       double eq_part = 0.0;
+      CPMPC_PARK();
+      DynConst P;
+      load_dyn_const(P, c.sm + k.off_dyn);
       for (int id = c.gl; id < k.nchunk; id += L) {
         const int s = id / cps, cc = id - s * cps;
         const int i0 = (cc * S) / cps, i1 = ((cc + 1) * S) / cps;
@@ -932,6 +981,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
           eq_part += fabs(e0) + fabs(e1) + fabs(e2) + fabs(e3);
         }
       }
+      CPMPC_PARK();
       if (cps > 1) {
         // stitch the chunks of a segment: Phi_s = Phi_{cps-1} ... Phi_0, Gamma_j <- (Phi_{cps-1} ... Phi_{cc+1}) Gamma_j
         CPMPC_GSYNC();
@@ -1097,15 +1147,28 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
     }
 
     // ---- line search (nonlinear.cc:351-443), groups of the warp in lock step ---------------------------------------
-    const double phi0 = f0 + penalty * eq0;
-    const double dphi0 = d_f + penalty * d_eq;
-    const double linf = fmax(fabs(d_f), fabs(d_eq));
-    int step_result = SR_MAX_ITERATIONS;
-    bool ls_done = !active;
-    double alpha = 1.0;
-    double a_prev = 0.0, phi_prev = 0.0, a_prev2 = 0.0, phi_prev2 = 0.0;
-    double step_f = 0.0, step_eq = 0.0;
-    int n_steps = 0;
+    double& phi0 = cold.phi0;
+    double& dphi0 = cold.dphi0;
+    double& linf = cold.linf;
+    phi0 = f0 + penalty * eq0;
+    dphi0 = d_f + penalty * d_eq;
+    linf = fmax(fabs(d_f), fabs(d_eq));
+    int& step_result = cold.step_result;
+    bool& ls_done = cold.ls_done;
+    double& alpha = cold.alpha;
+    double& a_prev = cold.a_prev;
+    double& phi_prev = cold.phi_prev;
+    double& a_prev2 = cold.a_prev2;
+    double& phi_prev2 = cold.phi_prev2;
+    double& step_f = cold.step_f;
+    double& step_eq = cold.step_eq;
+    int& n_steps = cold.n_steps;
+    step_result = SR_MAX_ITERATIONS;
+    ls_done = !active;
+    alpha = 1.0;
+    a_prev = phi_prev = a_prev2 = phi_prev2 = 0.0;
+    step_f = step_eq = 0.0;
+    n_steps = 0;
     double* lrow = (iter_log != nullptr && active) ? iter_log + (size_t)iter * CPMPC_ITERLOG_STRIDE : nullptr;
     for (int ls = 0; ls <= k.max_ls; ++ls) {
       if (__all_sync(0xffffffffu, ls_done)) break;
@@ -1149,7 +1212,9 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
         for (int col = c.gl; col < W; col += L)
           uc[col] = clampd(__dadd_rn(u[col], __dmul_rn(du[col], alpha)), -k.u_clamp, k.u_clamp);
         CPMPC_GSYNC();
-        evaluate_errors<L>(c, P, w, xc, uc, xkc, x_cur, set_point, u_prev, step_f, step_eq);
+        CPMPC_PARK();
+        evaluate_errors<L>(c, w, xc, uc, xkc, x_cur, set_point, u_prev, step_f, step_eq);
+        CPMPC_PARK();
         CPMPC_GSYNC();
         if (lrow != nullptr && c.gl == 0 && n_steps < 6) {
           lrow[9 + 3 * n_steps] = alpha;
@@ -1268,12 +1333,22 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
     const long long inst = round * n_groups + group_id;
     const bool have = inst < io.B;
 
-    DynConst P;
-    Weights w;
-    double x_cur[4] = {0.0, 0.0, 0.0, 0.0};
-    double set_point = 0.0;
+    // per-instance scalars that are only touched between the phases: parked like solve_group's (CPMPC_PARK)
+    struct KCold {
+      Weights w;
+      double x_cur[4];
+      double set_point, u_prev;
+      long long solves, sum_iter, sum_ls, sum_bad;
+      SolveResult res;
+    } kc;
+    asm volatile("" : : "l"(&kc) : "memory");
+    Weights& w = kc.w;
+    double(&x_cur)[4] = kc.x_cur;
+    double& set_point = kc.set_point;
+    x_cur[0] = x_cur[1] = x_cur[2] = x_cur[3] = 0.0;
+    set_point = 0.0;
     if (have) {
-      P = make_dyn_const(io.dyn + inst * CPMPC_DYN_STRIDE);
+      if (c.gl == 0) store_dyn_const(c.sm + cfg.off_dyn, make_dyn_const(io.dyn + inst * CPMPC_DYN_STRIDE));
       if (io.weights != nullptr) {
         const double* pw = io.weights + inst * CPMPC_WEIGHTS_STRIDE;
         w.w_u = pw[0];
@@ -1293,15 +1368,22 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
       for (int i = 0; i < 4; ++i) x_cur[i] = ps[i];
       set_point = io.set_points[inst];
     } else {
-      P = DynConst{1.0, 2.0, 1.0, 1.0, 2.0, 2.0, 0.0, 0.0, 1.0, 0.0, 1.0, 9.81};
+      if (c.gl == 0) store_dyn_const(c.sm + cfg.off_dyn, DynConst{1.0, 2.0, 1.0, 1.0, 2.0, 2.0, 0.0, 0.0, 1.0, 0.0, 1.0, 9.81});
       w.w_u = w.w_r = 1.0;
       w.wt[0] = w.wt[1] = w.wt[2] = w.wt[3] = 1.0;
     }
 
-    long long solves = 0, sum_iter = 0, sum_ls = 0, sum_bad = 0;
+    CPMPC_GSYNC();
+
+    long long& solves = kc.solves;
+    long long& sum_iter = kc.sum_iter;
+    long long& sum_ls = kc.sum_ls;
+    long long& sum_bad = kc.sum_bad;
+    solves = sum_iter = sum_ls = sum_bad = 0;
     for (long long step = 0; step < io.n_steps; ++step) {
       // ---- BuildProblem + initial guess (optimization.cc:44-71) ---------------------------------------------------
-      double u_prev = 0.0;
+      double& u_prev = kc.u_prev;
+      u_prev = 0.0;
       if (have) {
         double* prev = io.prev + inst * N;
         const bool warm = io.has_prev[inst] != 0;
@@ -1313,6 +1395,8 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
         if (c.gl == 0) {
           // FillInitialGuess: all shooting states re-integrated from x(0) (optimization.cc:333-351); the states at
           // the chunk boundaries inside a segment are kept for the first linearisation
+          DynConst Pl;
+          load_dyn_const(Pl, c.sm + cfg.off_dyn);
           double x[4] = {x_cur[0], x_cur[1], x_cur[2], x_cur[3]};
           double* xk = c.sm + cfg.off_xk;
 #pragma unroll
@@ -1328,7 +1412,7 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
                 ++cc;
                 nb = (cc < cfg.cps) ? (cc * S) / cfg.cps : S;
               }
-              rk4_step<false>(P, x, u[(s - 1) * S + i], cfg.dt);
+              rk4_step<false>(Pl, x, u[(s - 1) * S + i], cfg.dt);
               x[1] = mod_pi(x[1]);
             }
 #pragma unroll
@@ -1338,11 +1422,11 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
         CPMPC_GSYNC();
       }
 
-      SolveResult res;
+      SolveResult& res = kc.res;
       double* ilog = (io.iter_log != nullptr && have)
                          ? io.iter_log + (size_t)inst * cfg.max_iter * CPMPC_ITERLOG_STRIDE
                          : nullptr;
-      solve_group<L>(c, have, P, w, x_cur, set_point, u_prev, ilog, res);
+      solve_group<L>(c, have, w, x_cur, set_point, u_prev, ilog, res);
 
       if (have) {
         // ---- outputs (optimization.cc:83-96) ------------------------------------------------------------------
@@ -1356,10 +1440,12 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
           io.has_prev[inst] = 1;
           if (io.pred_out != nullptr) {
             // ComputePredictedStates (optimization.cc:353-371)
+            DynConst Pl;
+            load_dyn_const(Pl, c.sm + cfg.off_dyn);
             double x[4] = {x_cur[0], x_cur[1], x_cur[2], x_cur[3]};
             double* po = io.pred_out + (size_t)inst * W * 4;
             for (int q = 0; q < W; ++q) {
-              rk4_step<false>(P, x, u[q], cfg.dt);
+              rk4_step<false>(Pl, x, u[q], cfg.dt);
               x[1] = mod_pi(x[1]);
               po[4 * q] = x[0];
               po[4 * q + 1] = x[1];
@@ -1393,10 +1479,12 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
             const double u0 = u[0];
             if (io.controls_out != nullptr) io.controls_out[inst * io.n_steps + step] = u0;
             double dt = cfg.dt;
+            DynConst Pl;
+            load_dyn_const(Pl, c.sm + cfg.off_dyn);
             double x[4] = {x_cur[0], x_cur[1], x_cur[2], x_cur[3]};
             if (isfinite(u0)) {
               while (dt > 0.0) {
-                rk4_step<false>(P, x, u0, fmin(dt, 0.001));
+                rk4_step<false>(Pl, x, u0, fmin(dt, 0.001));
                 x[1] = mod_pi(x[1]);
                 dt -= 0.001;
               }
@@ -1430,6 +1518,7 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
 }
 
 #undef CPMPC_GSYNC
+#undef CPMPC_PARK
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Batched plant simulator: Simulator::Step (optimization/simulator.cc:11-36), one thread per plant.
