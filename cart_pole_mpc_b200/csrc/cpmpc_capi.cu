@@ -56,6 +56,7 @@ struct cpmpc_solver {
   unsigned char* d_has_prev = nullptr;
   double* d_u_guess = nullptr;
   double* d_kk = nullptr;
+  unsigned long long* d_queue = nullptr;
   double* d_iter_log = nullptr;
   bool log_enabled = false;
   // staging for the host-buffer entry points
@@ -132,6 +133,7 @@ int Launch(cpmpc_solver* h, KernelIO io, cudaStream_t stream) {
   io.prev = h->d_prev;
   io.has_prev = h->d_has_prev;
   io.kk_scratch = h->d_kk;
+  io.queue = h->d_queue;
   io.iter_log = h->log_enabled ? h->d_iter_log : nullptr;
   fn<<<h->grid, 32 * h->warps_per_block, h->smem_bytes, stream>>>(h->cfg, io);
   g_launches.fetch_add(1);
@@ -338,6 +340,8 @@ int cpmpc_create_ex(const cpmpc_params* params, int64_t batch, int device, uint3
   CUDA_TRY(cudaMemset(h->d_has_prev, 0, batch));
   CUDA_TRY(cudaMemset(h->d_prev, 0, sizeof(double) * batch * k.N));
   CUDA_TRY(cudaMalloc(&h->d_kk, sizeof(double) * n_groups * k.kk_stride));
+  CUDA_TRY(cudaMalloc(&h->d_queue, sizeof(unsigned long long) * 2));
+  CUDA_TRY(cudaMemset(h->d_queue, 0, sizeof(unsigned long long) * 2));
   CUDA_TRY(cudaMalloc(&h->d_u_guess, sizeof(double) * k.W));
   // cold-start sinusoid with the host's libm, exactly as optimization.cc:63-67 evaluates it
   std::vector<double> guess(k.W);
@@ -358,6 +362,7 @@ int cpmpc_destroy(cpmpc_handle h) {
   cudaFree(h->d_has_prev);
   cudaFree(h->d_u_guess);
   cudaFree(h->d_kk);
+  cudaFree(h->d_queue);
   cudaFree(h->d_iter_log);
   cudaFree(h->d_states);
   cudaFree(h->d_dyn);

@@ -67,6 +67,7 @@ struct KernelIO {
   cpmpc_stats* stats;        // [B] or nullptr
   double* iter_log;          // [B,max_iter,27] or nullptr
   double* kk_scratch;        // [n_groups, kk_stride]
+  unsigned long long* queue; // [2] work queue: next instance, warps finished (self-resetting)
   // closed loop (n_sim_steps > 0): the plant state is integrated forward with u[0] after every solve
   long long n_steps;         // number of Step()+Simulator::Step() rounds (1 and no plant update when sim == 0)
   int sim;                   // 1 = closed loop
@@ -1327,10 +1328,15 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
   double* xs = c.sm + cfg.off_xs;
   double* u = c.sm + cfg.off_u;
 
-  // every warp runs the same number of rounds so that warp-wide votes stay convergent
-  const long long rounds = (io.B + n_groups - 1) / n_groups;
-  for (long long round = 0; round < rounds; ++round) {
-    const long long inst = round * n_groups + group_id;
+  // Work queue: a warp takes G consecutive instances at a time, so warps that draw cheap instances (few line-search
+  // trials) go on instead of idling until the slowest warp of a static round is done.  Warp-wide votes stay
+  // convergent because all groups of a warp enter and leave a batch together.
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(io.queue, (unsigned long long)G);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= (unsigned long long)io.B) break;
+    const long long inst = (long long)base + g;
     const bool have = inst < io.B;
 
     // per-instance scalars that are only touched between the phases: parked like solve_group's (CPMPC_PARK)
@@ -1513,6 +1519,15 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
         atomicAdd((unsigned long long*)&io.stats_sum[2], (unsigned long long)sum_ls);
         atomicAdd((unsigned long long*)&io.stats_sum[3], (unsigned long long)sum_bad);
       }
+    }
+  }
+  // the last warp to drain the queue re-arms it for the next launch on this handle (launches are stream-ordered)
+  if (lane == 0) {
+    __threadfence();
+    const unsigned long long total = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
+    if (atomicAdd(io.queue + 1, 1ull) == total - 1) {
+      io.queue[0] = 0ull;
+      io.queue[1] = 0ull;
     }
   }
 }
