@@ -7,6 +7,8 @@
 #include <exception>
 
 #include "cartpole.hpp"
+#include "double_cartpole.hpp"
+#include "double_pendulum_gen.hpp"
 
 using namespace oracle;
 
@@ -33,7 +35,8 @@ OptimizationParams OptFromArray(const double* o) {
   return p;
 }
 
-void FillStats(const OptimizationOutputs& out, double* stats) {
+template <class Outputs>
+void FillStats(const Outputs& out, double* stats) {
   if (!stats) return;
   const auto& so = out.solver_outputs;
   stats[0] = static_cast<double>(static_cast<int>(so.termination_state));
@@ -46,7 +49,8 @@ void FillStats(const OptimizationOutputs& out, double* stats) {
   stats[7] = static_cast<double>(so.NumFailedLineSearches());
 }
 
-void FillIterLog(const OptimizationOutputs& out, std::size_t max_iterations, double* log) {
+template <class Outputs>
+void FillIterLog(const Outputs& out, std::size_t max_iterations, double* log) {
   if (!log) return;
   std::memset(log, 0, sizeof(double) * max_iterations * ORACLE_ITERLOG_STRIDE);
   const auto& its = out.solver_outputs.iterations;
@@ -283,6 +287,71 @@ int oracle_closed_loop(const double* opt, int64_t B, int64_t n_steps, double* st
   }
   if (term_hist_out) {
     for (int k = 0; k < 7; ++k) term_hist_out[k] += hist[k];
+  }
+  return threads;
+}
+
+// ---- double pendulum on a cart (double_cartpole.hpp) ---------------------------------------------------------------
+
+void oracle_dp_dynamics(const double* dyn, const double* x, double u, double* x_dot, double* J_x, double* J_u) {
+  DoublePendulumDynamics(dyn, x, u, x_dot, J_x, J_u);
+}
+
+void oracle_dp_rk4(const double* dyn, const double* x, double u, double h, double* x_new) {
+  DoubleRungeKutta4NoJacobians({dyn[0], dyn[1], dyn[2], dyn[3], dyn[4], dyn[5]}, x, u, h, x_new);
+}
+
+void oracle_dp_rk4_jac(const double* dyn, const double* x, double u, double h, double* x_new, double* D_x,
+                       double* D_u) {
+  DoubleRungeKutta4({dyn[0], dyn[1], dyn[2], dyn[3], dyn[4], dyn[5]}, x, u, h, x_new, D_x, D_u);
+}
+
+int oracle_dp_batch_step(const double* opt, int64_t B, const double* states, const double* dyn,
+                         const double* set_points, const double* weights, const double* prev,
+                         const uint8_t* has_prev, double* u_out, double* pred_out, double* sol_out, double* stats,
+                         double* iter_log, int n_threads) {
+  DoubleOptimizationParams base;
+  base.control_dt = opt[0];
+  base.window_length = static_cast<std::size_t>(opt[1]);
+  base.state_spacing = static_cast<std::size_t>(opt[2]);
+  base.max_iterations = static_cast<std::size_t>(opt[3]);
+  base.relative_exit_tol = opt[4];
+  base.absolute_first_derivative_tol = opt[5];
+  base.equality_penalty_initial = opt[6];
+  base.u_guess_sinusoid_amplitude = opt[7];
+  base.u_cost_weight = opt[8];
+  base.u_derivative_cost_weight = opt[9];
+  for (int i = 0; i < 6; ++i) base.final_cost_weight[i] = opt[10 + i];
+  const std::size_t W = base.window_length;
+  const std::size_t N = base.NumStates() * 6 + W;
+  const int threads = n_threads > 0 ? n_threads : omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 8) num_threads(threads)
+  for (int64_t i = 0; i < B; ++i) {
+    DoubleOptimizationParams p = base;
+    if (weights) {
+      const double* w = weights + i * ORACLE_DP_WEIGHTS_STRIDE;
+      p.u_cost_weight = w[0];
+      p.u_derivative_cost_weight = w[1];
+      for (int k = 0; k < 6; ++k) p.final_cost_weight[k] = w[2 + k];
+    }
+    try {
+      DoubleOptimization o(p);
+      if (prev && has_prev && has_prev[i]) {
+        o.SetPreviousSolution(std::vector<double>(prev + i * N, prev + (i + 1) * N));
+      }
+      const double* d = dyn + 6 * i;
+      const DoubleOptimizationOutputs out =
+          o.Step(states + 6 * i, {d[0], d[1], d[2], d[3], d[4], d[5]}, set_points[i]);
+      if (u_out) std::memcpy(u_out + i * W, out.u.data(), sizeof(double) * W);
+      if (pred_out) std::memcpy(pred_out + i * W * 6, out.predicted_states.data(), sizeof(double) * W * 6);
+      if (sol_out) std::memcpy(sol_out + i * N, o.previous_solution().data(), sizeof(double) * N);
+      FillStats(out, stats ? stats + i * ORACLE_STATS_STRIDE : nullptr);
+      FillIterLog(out, p.max_iterations, iter_log ? iter_log + i * p.max_iterations * ORACLE_ITERLOG_STRIDE : nullptr);
+    } catch (const std::exception&) {
+      if (stats) {
+        for (int k = 0; k < ORACLE_STATS_STRIDE; ++k) stats[i * ORACLE_STATS_STRIDE + k] = -1.0;
+      }
+    }
   }
   return threads;
 }

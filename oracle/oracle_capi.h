@@ -75,6 +75,21 @@ int oracle_closed_loop(const double* opt, int64_t B, int64_t n_steps, double* st
                        const double* set_points, double* controls_out, double* last_pred_terminal_out,
                        int64_t* counts_out, int64_t* term_hist_out, int n_threads);
 
+/* ---- double pendulum on a cart: nx = 6 generalisation (oracle/double_cartpole.hpp; the reference has only the
+ * physics spec symbolic/dynamics_double.py).  opt[16] = the first ten entries as above, then the six terminal
+ * weights in state order [b_x, th_1, th_2, b_x', th_1', th_2'] (negative = hard equality).  dyn[6] =
+ * {m_b, m_1, m_2, l_1, l_2, g}.  x[6] = [b_x, th_1, th_2, b_x', th_1', th_2']. */
+#define ORACLE_DP_WEIGHTS_STRIDE 8 /* u, u_derivative, then the six terminal weights */
+void oracle_dp_dynamics(const double* dyn, const double* x, double u, double* x_dot, double* J_x, double* J_u);
+void oracle_dp_rk4(const double* dyn, const double* x, double u, double h, double* x_new);
+void oracle_dp_rk4_jac(const double* dyn, const double* x, double u, double h, double* x_new, double* D_x,
+                       double* D_u);
+/* Same contract as oracle_batch_step with states B*6, dyn B*6, pred_out B*W*6, N = 6*NS + W. */
+int oracle_dp_batch_step(const double* opt, int64_t B, const double* states, const double* dyn,
+                         const double* set_points, const double* weights, const double* prev,
+                         const uint8_t* has_prev, double* u_out, double* pred_out, double* sol_out, double* stats,
+                         double* iter_log, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

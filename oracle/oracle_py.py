@@ -90,6 +90,14 @@ def lib() -> C.CDLL:
         L.oracle_closed_loop.restype = C.c_int
         L.oracle_closed_loop.argtypes = [dp, C.c_int64, C.c_int64, dp, dp, dp, dp, dp, C.POINTER(C.c_int64),
                                          C.POINTER(C.c_int64), C.c_int]
+        L.oracle_dp_dynamics.restype = None
+        L.oracle_dp_dynamics.argtypes = [dp, dp, C.c_double, dp, dp, dp]
+        L.oracle_dp_rk4.restype = None
+        L.oracle_dp_rk4.argtypes = [dp, dp, C.c_double, C.c_double, dp]
+        L.oracle_dp_rk4_jac.restype = None
+        L.oracle_dp_rk4_jac.argtypes = [dp, dp, C.c_double, C.c_double, dp, dp, dp]
+        L.oracle_dp_batch_step.restype = C.c_int
+        L.oracle_dp_batch_step.argtypes = L.oracle_batch_step.argtypes
         _lib = L
     return _lib
 
@@ -194,6 +202,70 @@ def batch_step(opt, states, dyn, set_points, weights=None, prev=None, has_prev=N
         hp = has_prev.ctypes.data_as(C.POINTER(C.c_uint8))
     threads = lib().oracle_batch_step(_p(opt), B, _p(states), _p(dyn), _p(set_points), _p(weights), _p(prev), hp,
                                       _p(u), _p(pred), _p(sol), _p(stats), _p(ilog), int(n_threads))
+    return BatchResult(u, pred, sol, stats, ilog, threads)
+
+
+# ---- double pendulum on a cart (oracle/double_cartpole.hpp) ---------------------------------------------------------
+DP_NX = 6
+DP_WEIGHTS_STRIDE = 8
+DP_OPT_FIELDS = OPT_FIELDS[:10] + ("b_x_final_cost_weight", "th_1_final_cost_weight", "th_2_final_cost_weight",
+                                   "b_x_dot_final_cost_weight", "th_1_dot_final_cost_weight",
+                                   "th_2_dot_final_cost_weight")
+DP_OPT_DEFAULTS = OPT_DEFAULTS[:10] + (150.0, -1.0, -1.0, -1.0, -1.0, -1.0)
+
+
+def dp_opt_array(**overrides) -> np.ndarray:
+    vals = dict(zip(DP_OPT_FIELDS, DP_OPT_DEFAULTS))
+    for k, v in overrides.items():
+        if k not in vals:
+            raise KeyError(k)
+        vals[k] = v
+    return np.asarray([float(vals[k]) for k in DP_OPT_FIELDS], dtype=np.float64)
+
+
+def dp_dynamics(dyn, x, u, jacobians=True):
+    dyn, x = _f64(dyn), _f64(x)
+    xdot = np.zeros(6)
+    Jx = np.zeros((6, 6)) if jacobians else None
+    Ju = np.zeros(6) if jacobians else None
+    lib().oracle_dp_dynamics(_p(dyn), _p(x), float(u), _p(xdot), _p(Jx), _p(Ju))
+    return (xdot, Jx, Ju) if jacobians else xdot
+
+
+def dp_rk4(dyn, x, u, h):
+    dyn, x = _f64(dyn), _f64(x)
+    out = np.zeros(6)
+    lib().oracle_dp_rk4(_p(dyn), _p(x), float(u), float(h), _p(out))
+    return out
+
+
+def dp_rk4_jac(dyn, x, u, h):
+    dyn, x = _f64(dyn), _f64(x)
+    out, Dx, Du = np.zeros(6), np.zeros((6, 6)), np.zeros(6)
+    lib().oracle_dp_rk4_jac(_p(dyn), _p(x), float(u), float(h), _p(out), _p(Dx), _p(Du))
+    return out, Dx, Du
+
+
+def dp_batch_step(opt, states, dyn, set_points, weights=None, prev=None, has_prev=None, n_threads=0,
+                  want_iter_log=True) -> BatchResult:
+    opt = _f64(opt)
+    states, dyn, set_points = _f64(states), _f64(dyn), _f64(set_points)
+    B = states.shape[0]
+    W, S, max_it = int(opt[1]), int(opt[2]), int(opt[3])
+    N = (W // S + 1) * DP_NX + W
+    u = np.zeros((B, W))
+    pred = np.zeros((B, W, DP_NX))
+    sol = np.zeros((B, N))
+    stats = np.zeros((B, STATS_STRIDE))
+    ilog = np.zeros((B, max_it, ITERLOG_STRIDE)) if want_iter_log else None
+    weights = _f64(weights) if weights is not None else None
+    prev = _f64(prev) if prev is not None else None
+    hp = None
+    if has_prev is not None:
+        has_prev = np.ascontiguousarray(np.asarray(has_prev, dtype=np.uint8))
+        hp = has_prev.ctypes.data_as(C.POINTER(C.c_uint8))
+    threads = lib().oracle_dp_batch_step(_p(opt), B, _p(states), _p(dyn), _p(set_points), _p(weights), _p(prev), hp,
+                                         _p(u), _p(pred), _p(sol), _p(stats), _p(ilog), int(n_threads))
     return BatchResult(u, pred, sol, stats, ilog, threads)
 
 
