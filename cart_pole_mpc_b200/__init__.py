@@ -8,5 +8,7 @@ the reference's struct/class API.  Importing this package never touches oracle/.
 from .batched import (BatchedOptimization, StepOutputs, TERMINATION_NAMES, STEP_RESULT_NAMES, make_params,
                       measure_fp64_peak, sim_step, launch_count)
 
-__all__ = ["BatchedOptimization", "StepOutputs", "TERMINATION_NAMES", "STEP_RESULT_NAMES", "make_params",
+from .plant import PlantBatchedOptimization, make_plant_params
+
+__all__ = ["PlantBatchedOptimization", "make_plant_params", "BatchedOptimization", "StepOutputs", "TERMINATION_NAMES", "STEP_RESULT_NAMES", "make_params",
            "measure_fp64_peak", "sim_step", "launch_count"]

@@ -21,7 +21,32 @@ EXPORTED_SYMBOLS = (
     "cpmpc_get_previous_solution", "cpmpc_enable_iteration_log", "cpmpc_get_iteration_log", "cpmpc_sim_step_device",
     "cpmpc_sim_step", "cpmpc_closed_loop", "cpmpc_closed_loop_device", "cpmpc_launch_count",
     "cpmpc_measure_fp64_peak",
+    "cpmpc_plant_state_dim", "cpmpc_plant_dyn_dim", "cpmpc_plant_default_params", "cpmpc_plant_create",
+    "cpmpc_plant_destroy", "cpmpc_plant_solution_dim", "cpmpc_plant_step", "cpmpc_plant_step_device",
+    "cpmpc_plant_reset", "cpmpc_plant_reset_device", "cpmpc_plant_set_previous_solution",
+    "cpmpc_plant_get_previous_solution", "cpmpc_plant_enable_iteration_log", "cpmpc_plant_get_iteration_log",
 )
+
+PLANT_SINGLE = 0  # CPMPC_PLANT_SINGLE
+PLANT_DOUBLE = 1  # CPMPC_PLANT_DOUBLE
+PLANT_MAX_NX = 6
+
+
+class CpmpcPlantParams(C.Structure):
+    """struct cpmpc_plant_params: OptimizationParams with the terminal weights as an array in state order."""
+    _fields_ = [
+        ("control_dt", C.c_double),
+        ("window_length", C.c_int64),
+        ("state_spacing", C.c_int64),
+        ("max_iterations", C.c_int64),
+        ("relative_exit_tol", C.c_double),
+        ("absolute_first_derivative_tol", C.c_double),
+        ("equality_penalty_initial", C.c_double),
+        ("u_guess_sinusoid_amplitude", C.c_double),
+        ("u_cost_weight", C.c_double),
+        ("u_derivative_cost_weight", C.c_double),
+        ("final_cost_weight", C.c_double * PLANT_MAX_NX),
+    ]
 
 
 class CpmpcParams(C.Structure):
@@ -128,6 +153,34 @@ def lib() -> C.CDLL:
     L.cpmpc_launch_count.argtypes = []
     L.cpmpc_measure_fp64_peak.restype = C.c_int
     L.cpmpc_measure_fp64_peak.argtypes = [C.c_int, dp]
+    L.cpmpc_plant_state_dim.restype = C.c_int
+    L.cpmpc_plant_state_dim.argtypes = [C.c_int]
+    L.cpmpc_plant_dyn_dim.restype = C.c_int
+    L.cpmpc_plant_dyn_dim.argtypes = [C.c_int]
+    L.cpmpc_plant_default_params.restype = None
+    L.cpmpc_plant_default_params.argtypes = [C.c_int, C.POINTER(CpmpcPlantParams)]
+    L.cpmpc_plant_create.restype = C.c_int
+    L.cpmpc_plant_create.argtypes = [C.c_int, C.POINTER(CpmpcPlantParams), C.c_int64, C.c_int, C.POINTER(vp)]
+    L.cpmpc_plant_destroy.restype = C.c_int
+    L.cpmpc_plant_destroy.argtypes = [vp]
+    L.cpmpc_plant_solution_dim.restype = C.c_int64
+    L.cpmpc_plant_solution_dim.argtypes = [vp]
+    L.cpmpc_plant_step.restype = C.c_int
+    L.cpmpc_plant_step.argtypes = [vp] * 8
+    L.cpmpc_plant_step_device.restype = C.c_int
+    L.cpmpc_plant_step_device.argtypes = [vp] * 9
+    L.cpmpc_plant_reset.restype = C.c_int
+    L.cpmpc_plant_reset.argtypes = [vp]
+    L.cpmpc_plant_reset_device.restype = C.c_int
+    L.cpmpc_plant_reset_device.argtypes = [vp, vp]
+    L.cpmpc_plant_set_previous_solution.restype = C.c_int
+    L.cpmpc_plant_set_previous_solution.argtypes = [vp, vp]
+    L.cpmpc_plant_get_previous_solution.restype = C.c_int
+    L.cpmpc_plant_get_previous_solution.argtypes = [vp, vp, vp]
+    L.cpmpc_plant_enable_iteration_log.restype = C.c_int
+    L.cpmpc_plant_enable_iteration_log.argtypes = [vp, C.c_int]
+    L.cpmpc_plant_get_iteration_log.restype = C.c_int
+    L.cpmpc_plant_get_iteration_log.argtypes = [vp, vp]
     _lib = L
     return L
 

@@ -12,13 +12,14 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libcpmpc.so")
-SOURCES = ["cpmpc_capi.cu"]
-HEADERS = ["solver_kernel.cuh", "dynamics.cuh", "fastmath.cuh", os.path.join("..", "..", "include", "cpmpc.h")]
+SOURCES = ["cpmpc_capi.cu", "cpmpc_plant_capi.cu"]
+HEADERS = ["solver_kernel.cuh", "plant_solver_kernel.cuh", "double_pendulum.cuh", "dynamics.cuh", "fastmath.cuh",
+           "capi_common.hpp", os.path.join("..", "..", "include", "cpmpc.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fPIC",
 ]
 
 
@@ -43,16 +44,31 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile the library if it is missing or older than its sources; returns its path."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
     env = dict(os.environ)
     # the image's CXX points at a wrapper without OpenMP; nvcc only needs a plain host g++
     env.pop("CXX", None)
     env.pop("CC", None)
-    proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True, env=env)
+    # one nvcc per translation unit, side by side; objects are only rebuilt when older than any source or header
+    newest = max(os.path.getmtime(os.path.join(CSRC, f)) for f in SOURCES + HEADERS)
+    objs, procs = [], []
+    for src in SOURCES:
+        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > newest:
+            continue
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        procs.append(subprocess.Popen(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                                      env=env))
+    for proc in procs:
+        out, _ = proc.communicate()
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + out)
+        if verbose:
+            print(out)
+    proc = subprocess.run([_nvcc(), "-shared", "-o", LIB_PATH] + objs, cwd=CSRC, capture_output=True, text=True,
+                          env=env)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
-    if verbose:
-        print(proc.stderr)
+        raise RuntimeError("nvcc link failed:\n" + proc.stdout + proc.stderr)
     return LIB_PATH
 
 

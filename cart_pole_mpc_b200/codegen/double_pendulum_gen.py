@@ -204,6 +204,17 @@ struct DpConst {
   double mt, h1, h2, a11, a12, a22, g1, g2;
 };
 
+// The branch-free sincos of fastmath.cuh is valid for |x| < 2^20.  This undamped model blows up in finite time along
+// rejected line-search trials (angles of 1e100 and beyond, which the reference-style solver survives because libm
+// still returns finite values there: the trial is simply rejected), so huge arguments take CUDA's full-range sincos.
+__device__ __forceinline__ void dp_sincos(const double x, double& s, double& c) {
+  if (fabs(x) < 1048576.0) {
+    fm::sincos_bf(x, s, c);
+  } else {
+    ::sincos(x, &s, &c);
+  }
+}
+
 // p = DoubleCartPoleParams {m_b, m_1, m_2, l_1, l_2, g} (dynamics_double.py:13-22)
 __device__ __forceinline__ DpConst make_dp_const(const double* __restrict__ p) {
   const double m_b = p[0], m_1 = p[1], m_2 = p[2], l_1 = p[3], l_2 = p[4], g = p[5];
@@ -218,8 +229,8 @@ __device__ __forceinline__ void dp_eval(const DpConst& P, const double th_1, con
                                         const double th_2d, const double u, double acc[3], double J_th1[3],
                                         double J_th2[3], double J_w1[3], double J_w2[3], double J_u[3]) {
   double s1, c1, s2, c2;
-  fm::sincos(th_1, s1, c1);
-  fm::sincos(th_2, s2, c2);""")
+  dp_sincos(th_1, s1, c1);
+  dp_sincos(th_2, s2, c2);""")
     out += body
     out.append("  if (JAC) {")
     out += jac

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/cpmpc.h"
+#include "capi_common.hpp"
 #include "solver_kernel.cuh"
 
 using namespace cpmpc;
@@ -40,6 +41,13 @@ int Pow2Ceil(int v) {
 }
 
 }  // namespace
+
+namespace cpmpc {
+namespace detail {
+int Fail(int code, const std::string& msg) { return ::Fail(code, msg); }
+void CountLaunches(int n) { g_launches.fetch_add(n); }
+}  // namespace detail
+}  // namespace cpmpc
 
 struct cpmpc_solver {
   cpmpc_params params;

@@ -73,3 +73,28 @@ def sweep_batch(batch: int, seed: int = SEED_CONFIG2 + 2, first: int = 0, dyn=DE
     weights[:, 3:] = -1.0
     set_points = uniform(seed, first, batch, 12, -1.0, 1.0)
     return states, params, np.ascontiguousarray(set_points), weights
+
+
+# symbolic/dynamics_double.py:13-22 field order {m_b, m_1, m_2, l_1, l_2, g}; both poles like the single pendulum's
+DEFAULT_DOUBLE_DYN = (1.0, 0.1, 0.1, 0.25, 0.25, 9.81)
+
+
+def double_swingup_batch(batch: int, seed: int = SEED_CONFIG2 + 4, first: int = 0, dyn=DEFAULT_DOUBLE_DYN):
+    """Config 5: cart-mounted double pendulum, randomised states around hanging-down (both angles near -pi/2) and
+    randomised cart / pole masses (the single pendulum's slider ranges, application.ts:223-240, for both poles).
+
+    Returns (states[B,6] = [b_x, th_1, th_2, b_x', th_1', th_2'], dyn_params[B,6], set_points[B]).
+    """
+    states = np.empty((batch, 6), dtype=np.float64)
+    states[:, 0] = uniform(seed, first, batch, 0, -0.5, 0.5)
+    states[:, 1] = -math.pi / 2 + uniform(seed, first, batch, 1, -0.5, 0.5)
+    states[:, 2] = -math.pi / 2 + uniform(seed, first, batch, 2, -0.5, 0.5)
+    states[:, 3] = uniform(seed, first, batch, 3, -0.5, 0.5)
+    states[:, 4] = uniform(seed, first, batch, 4, -1.0, 1.0)
+    states[:, 5] = uniform(seed, first, batch, 5, -1.0, 1.0)
+    params = np.tile(np.asarray(dyn, dtype=np.float64), (batch, 1))
+    params[:, 0] = uniform(seed, first, batch, 6, 0.1, 2.0)   # m_b
+    params[:, 1] = uniform(seed, first, batch, 7, 0.1, 1.0)   # m_1
+    params[:, 2] = uniform(seed, first, batch, 8, 0.1, 1.0)   # m_2
+    set_points = np.zeros(batch, dtype=np.float64)
+    return np.ascontiguousarray(states), np.ascontiguousarray(params), set_points

@@ -170,6 +170,63 @@ int64_t cpmpc_launch_count(void);
  * it in *tflops_out (2 flops per FMA).  Used as the roofline denominator (MEASURED_PEAKS.json has no FP64 entry). */
 int cpmpc_measure_fp64_peak(int device, double* tflops_out);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Plant-generic entry points: the same controller over a plant with NX states per shooting node.  They exist for the
+ * cart-mounted DOUBLE pendulum (BASELINE.json configs[4]).  The reference holds only its physics spec
+ * (symbolic/dynamics_double.py:25-148; DoubleCartPoleParams at :13-22) and a TODO in the optimiser
+ * (optimization/optimization.cc:197-199): there is no reference interface to replace, so these mirror the
+ * single-pendulum entry points above with NX-wide arrays.  CPMPC_PLANT_SINGLE runs the single pendulum through the
+ * same generic kernels (a cross-check of the generic code against the single-pendulum path; cpmpc_create is the tuned
+ * path for it).
+ *   state  x = [q, q']: single [b_x, th_1, b_x', th_1'] (NX = 4); double [b_x, th_1, th_2, b_x', th_1', th_2'] (NX = 6)
+ *   dyn    single: SingleCartPoleParams (9 doubles); double: {m_b, m_1, m_2, l_1, l_2, g} (6 doubles)
+ *   N = NX*NS + W; terminal targets: b_x -> set point, every angle -> +pi/2 (upright), every rate -> 0.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define CPMPC_PLANT_SINGLE 0
+#define CPMPC_PLANT_DOUBLE 1
+#define CPMPC_PLANT_MAX_NX 6
+#define CPMPC_DP_STATE_STRIDE 6
+#define CPMPC_DP_DYN_STRIDE 6   /* DoubleCartPoleParams, symbolic/dynamics_double.py:13-22 */
+#define CPMPC_DP_WEIGHTS_STRIDE 8 /* u, u_derivative, then the six terminal weights in state order */
+
+typedef struct cpmpc_plant_params {
+  double control_dt;                    /* 0.01 */
+  int64_t window_length;                /* 40 */
+  int64_t state_spacing;                /* 10 */
+  int64_t max_iterations;               /* 8 */
+  double relative_exit_tol;             /* 1e-5 */
+  double absolute_first_derivative_tol; /* 1e-6 */
+  double equality_penalty_initial;      /* 1.0 */
+  double u_guess_sinusoid_amplitude;    /* 10.0 */
+  double u_cost_weight;                 /* 0.1 */
+  double u_derivative_cost_weight;      /* 0.1 */
+  double final_cost_weight[CPMPC_PLANT_MAX_NX]; /* state order; negative => hard equality; 150 for b_x, -1 else */
+} cpmpc_plant_params;
+
+typedef struct cpmpc_plant_solver* cpmpc_plant_handle;
+
+int cpmpc_plant_state_dim(int plant);  /* NX, or -1 for an unknown plant */
+int cpmpc_plant_dyn_dim(int plant);    /* doubles of dynamics parameters per instance */
+void cpmpc_plant_default_params(int plant, cpmpc_plant_params* params);
+int cpmpc_plant_create(int plant, const cpmpc_plant_params* params, int64_t batch, int device,
+                       cpmpc_plant_handle* out);
+int cpmpc_plant_destroy(cpmpc_plant_handle h);
+int64_t cpmpc_plant_solution_dim(cpmpc_plant_handle h); /* N */
+/* Step for all B instances, HOST buffers, synchronous: states [B*NX], dyn_params [B*dyn_dim], set_points [B],
+ * weights [B*(2+NX)] or NULL, u_out [B*W], pred_out [B*W*NX] or NULL, stats_out [B] or NULL. */
+int cpmpc_plant_step(cpmpc_plant_handle h, const double* states, const double* dyn_params, const double* set_points,
+                     const double* weights, double* u_out, double* pred_out, cpmpc_stats* stats_out);
+/* DEVICE pointers, asynchronous on `stream`. */
+int cpmpc_plant_step_device(cpmpc_plant_handle h, const double* states, const double* dyn_params,
+                            const double* set_points, const double* weights, double* u_out, double* pred_out,
+                            cpmpc_stats* stats_out, void* stream);
+int cpmpc_plant_reset(cpmpc_plant_handle h);                      /* Reset() of every instance */
+int cpmpc_plant_reset_device(cpmpc_plant_handle h, void* stream); /* same, ordered on `stream` */
+int cpmpc_plant_set_previous_solution(cpmpc_plant_handle h, const double* solutions);          /* HOST [B*N] */
+int cpmpc_plant_get_previous_solution(cpmpc_plant_handle h, double* solutions_out, uint8_t* has_prev_out);
+int cpmpc_plant_enable_iteration_log(cpmpc_plant_handle h, int enable);
+int cpmpc_plant_get_iteration_log(cpmpc_plant_handle h, double* log_out);
+
 #ifdef __cplusplus
 }
 #endif

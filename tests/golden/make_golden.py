@@ -51,6 +51,15 @@ def main():
     st, dy, sp, w = synthetic.sweep_batch(32)
     save("sweep_sample32.npz", oracle_py.opt_array(), st, dy, sp, weights=w)
 
+    # config 5: cart-mounted double pendulum (the reference has no implementation: oracle/double_cartpole.hpp)
+    st, dy, sp = synthetic.double_swingup_batch(48)
+    opt5 = oracle_py.dp_opt_array()
+    res = oracle_py.dp_batch_step(opt5, st, dy, sp)
+    np.savez_compressed(os.path.join(HERE, "config5_double_sample48.npz"), opt=opt5, states=st, dyn=dy,
+                        set_points=sp, u=res.u, predicted=res.predicted, solution=res.solution, stats=res.stats,
+                        iter_log=res.iter_log)
+    print("config5_double_sample48.npz term hist", np.bincount(res.termination, minlength=7).tolist())
+
     # closed loop (optimization_test.cc:12-77): 200 steps, controls and final state
     opt = oracle_py.opt_array(state_spacing=5, max_iterations=10)
     states, controls, term, counts, hist, _ = oracle_py.closed_loop(
