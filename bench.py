@@ -31,15 +31,16 @@ DEFAULT_BATCH = 4096
 # ----------------------------------------------------------------------------------------------------------------------
 # Algorithmic flop count of one solve, SURVEY.md section 8(d) (FMA = 2 flops, sin/cos/tanh/sqrt/div/fmod = 1 flop).
 # ----------------------------------------------------------------------------------------------------------------------
-def algorithmic_flops(n_iter, n_ls, W=40, S=10, n_te=3, n_cost=81):
-    nx = 4
+def algorithmic_flops(n_iter, n_ls, W=40, S=10, n_te=3, n_cost=81, nx=4, C_f=76, C_fJ=198):
+    """nx=4 constants are SURVEY.md 8(d)'s.  For the double pendulum (nx=6) the same formula is used with the operation
+    counts of the generated dynamics (csrc/double_pendulum.cuh: value 60 mul + 24 add + 1 div + 4 libm = 89, with
+    Jacobians + 175 = 264) and the chain-rule / backward-sweep terms scaled by (nx/4)^3 from their nx=4 values."""
     NS = W // S + 1
     N = nx * NS + W
     K = nx * (NS - 1) + nx + n_te
-    C_fJ, C_f = 198, 76
-    C_rkJ = 4 * C_fJ + 710
-    C_rk = 4 * C_f + 60
-    C_bwd = 140
+    C_rkJ = 4 * C_fJ + 710 * (nx / 4) ** 3
+    C_rk = 4 * C_f + 15 * nx
+    C_bwd = 140 * (nx / 4) ** 3
     F_lin = W * (C_rkJ + C_bwd) + 6 * n_cost
     F_merit = W * C_rk + 3 * n_cost + 2 * K
     F_roll = W * C_rk
@@ -384,6 +385,98 @@ def run_sweep(args):
     return 0
 
 
+def run_double(args):
+    """configs[4]: double pendulum on a cart (nx=6), 262144 instances in total (strong scaling: 262144 / N per GPU),
+    cold start, through the plant-generic kernels (csrc/plant_solver_kernel.cuh)."""
+    import torch
+    from cart_pole_mpc_b200 import PlantBatchedOptimization, measure_fp64_peak, launch_count, synthetic, _capi
+    world, rank, local_rank, dist, dev = _dist_setup()
+    total = args.batch if args.batch != DEFAULT_BATCH else 262144
+    B = total // world
+    W, S, nx = 40, 10, 6
+    st_h, dy_h, sp_h = synthetic.double_swingup_batch(B, first=rank * B)
+    solver = PlantBatchedOptimization("double", B, device=local_rank)
+    to = lambda a: torch.from_numpy(a).to(dev)
+    st_d, dy_d, sp_d = to(st_h), to(dy_h), to(sp_h)
+    u_d = torch.empty((B, W), dtype=torch.float64, device=dev)
+    pred_d = torch.empty((B, W, nx), dtype=torch.float64, device=dev)
+    stats_d = torch.empty((B, 56), dtype=torch.uint8, device=dev)
+
+    def one_step():
+        solver.reset_device()
+        solver.step_device(st_d, dy_d, sp_d, u_d, pred_out=pred_d, stats_out=stats_d)
+
+    steps = max(1, min(args.steps, 10))
+    warm = max(1, min(args.warmup, 3))
+    for _ in range(warm):
+        one_step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one_step()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    total_ms = e0.elapsed_time(e1)
+    launches = launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    stats = np.frombuffer(stats_d.cpu().numpy().tobytes(), dtype=_capi.STATS_DTYPE)
+    flops = float(algorithmic_flops(stats["n_iterations"].astype(np.float64), stats["n_line_search_steps"].astype(np.float64),
+                                    W=W, S=S, n_te=5, n_cost=1 + 2 * W, nx=nx, C_f=89, C_fJ=264).sum())
+    (total_ms,) = _max_over_ranks(dist, dev, [total_ms])
+    (flops_all,) = _sum_over_ranks(dist, dev, [flops])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+    peak = measure_fp64_peak(local_rank)
+    ms = total_ms / steps
+    hist = np.bincount(np.maximum(stats["termination_state"], 0), minlength=7).tolist()
+    line = {
+        "metric": "batched MPC solves/sec (FP64), double pendulum on a cart, cold start", "value": world * B / (ms * 1e-3),
+        "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{world * B}-instance double-pendulum-on-cart batch ({B} per GPU), nx=6, W=40 S=10 "
+                               "max_iter=8, randomized initial states and masses (BASELINE.json configs[4])",
+                   "batch_per_gpu": B, "qp": "plant-generic segment-wise Riccati / condensed",
+                   "l2": f"results {B * (W * (nx + 1) * 8 + 56) / 1e6:.0f} MB per step exceed L2" if B >= 65536 else
+                         "working set fits L2; warm start reset between steps"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "fp64", "achieved": flops_all / (ms * 1e-3) / 1e12 / world, "peak": peak, "unit": "TFLOP/s",
+                     "frac": flops_all / (ms * 1e-3) / 1e12 / world / peak, "traffic": None,
+                     "flops_model": "SURVEY.md 8(d) formula with nx=6 and the generated dynamics' operation counts "
+                                    "(C_f=89, C_fJ=264), per GPU"},
+        "mean_sqp_iterations": float(stats["n_iterations"].mean()),
+        "mean_merit_evaluations": float(stats["n_line_search_steps"].mean()), "termination_hist": hist,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import oracle_py
+        nb = min(B, 2048)
+        t0 = time.perf_counter()
+        ora = oracle_py.dp_batch_step(oracle_py.dp_opt_array(), st_h[:nb], dy_h[:nb], sp_h[:nb], want_iter_log=False)
+        dt_cpu = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": nb / dt_cpu, "unit": UNIT, "cores": int(ora.threads), "kind": "port",
+                                "sample": f"the first {nb} instances, one instance per thread (nx=6 oracle; the "
+                                          "reference has no optimiser for this plant)"}
+        g = stats["f"][:nb] + stats["penalty"][:nb] * stats["equality"][:nb]
+        rel = np.abs(g - ora.merit) / np.maximum(np.abs(ora.merit), 1e-300)
+        line["parity"] = {"frac_within_1e-8_rel_cost": float((rel <= 1e-8).mean()),
+                          "iteration_count_match": float((stats["n_iterations"][:nb] == ora.n_iterations).mean()),
+                          "termination_match": float((stats["termination_state"][:nb] == ora.termination).mean())}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -394,8 +487,8 @@ def main():
     ap.add_argument("--allgather", action="store_true",
                     help="also all-gather u and stats across ranks inside the timed region (NCCL)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4"],
-                    help="config2: the headline bench (default); config3: closed loop; config4: long-horizon sweep")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"],
+                    help="config2: the headline bench (default); config3: closed loop; config4: long-horizon sweep; config5: double pendulum on a cart")
     ap.add_argument("--cl-steps", type=int, default=500, help="control steps of the closed loop (config3)")
     ap.add_argument("--test-variant", action="store_true", help="config3 with optimization_test.cc's S=5, max_iter=10")
     args = ap.parse_args()
@@ -403,6 +496,8 @@ def main():
         return run_closed_loop(args)
     if args.impl != "reference" and args.workload == "config4":
         return run_sweep(args)
+    if args.impl != "reference" and args.workload == "config5":
+        return run_double(args)
 
     if args.impl == "reference":
         if args.steps > 20:
