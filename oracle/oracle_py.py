@@ -5,6 +5,7 @@ Never imported by the product package (cart_pole_mpc_b200).
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 import subprocess
@@ -46,13 +47,58 @@ def build(force: bool = False) -> str:
 
 
 _lib = None
+_ref_lib = None
+_use_ref = False
+
+# oracle/_ref/libref.so: the reference's own translation units compiled against oracle/eigen_shim (Makefile target
+# `ref`).  It can only be BUILT where /root/reference exists (the build container); the built file is git-ignored
+# but travels to the GPU box with the repo snapshot.
+_REF_LIB_PATH = os.path.join(_HERE, "_ref", "libref.so")
+REFERENCE_ROOT = os.environ.get("CPMPC_REFERENCE_ROOT", "/root/reference")
+
+
+def ref_available() -> bool:
+    return os.path.exists(_REF_LIB_PATH)
+
+
+def build_ref(force: bool = False) -> str | None:
+    """Compile oracle/_ref/libref.so from the reference's sources where they lie.  Returns None (and builds nothing)
+    when the reference tree is absent, e.g. on the GPU box."""
+    if not os.path.isdir(os.path.join(REFERENCE_ROOT, "optimization")):
+        return _REF_LIB_PATH if ref_available() else None
+    if force or not ref_available():
+        subprocess.run(["make", "-C", _HERE, "ref", f"REF={REFERENCE_ROOT}"], check=True, capture_output=True)
+    return _REF_LIB_PATH
+
+
+@contextlib.contextmanager
+def using_ref():
+    """Route every function of this module that exists in libref.so (dynamics, rk4, sim_step, qp_nullspace,
+    Optimization, batch_step, closed_loop) to the compiled reference instead of the restatement."""
+    global _use_ref
+    if not ref_available():
+        raise FileNotFoundError(_REF_LIB_PATH)
+    old, _use_ref = _use_ref, True
+    try:
+        yield
+    finally:
+        _use_ref = old
 
 
 def lib() -> C.CDLL:
-    global _lib
+    global _lib, _ref_lib
+    if _use_ref:
+        if _ref_lib is None:
+            _ref_lib = _bind(C.CDLL(_REF_LIB_PATH), full=False)
+        return _ref_lib
     if _lib is None:
         build()
-        L = C.CDLL(_LIB_PATH)
+        _lib = _bind(C.CDLL(_LIB_PATH), full=True)
+    return _lib
+
+
+def _bind(L: C.CDLL, full: bool) -> C.CDLL:
+    if True:
         dp = C.POINTER(C.c_double)
         L.oracle_mod_pi.restype = C.c_double
         L.oracle_mod_pi.argtypes = [C.c_double]
@@ -66,12 +112,17 @@ def lib() -> C.CDLL:
         L.oracle_sim_step.argtypes = [dp, dp, C.c_double, C.c_double, dp, dp]
         L.oracle_qp_nullspace.restype = C.c_int
         L.oracle_qp_nullspace.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp]
+        if not full:
+            L.oracle_ref_info.restype = C.c_char_p
+            L.oracle_ref_info.argtypes = []
+    if full:
         L.oracle_quadratic_approx_minimum.restype = C.c_int
         L.oracle_quadratic_approx_minimum.argtypes = [C.c_double] * 4 + [dp]
         L.oracle_cubic_approx_coeffs.restype = None
         L.oracle_cubic_approx_coeffs.argtypes = [C.c_double] * 6 + [dp]
         L.oracle_cubic_approx_minimum.restype = C.c_int
         L.oracle_cubic_approx_minimum.argtypes = [C.c_double, dp, dp]
+    if True:
         L.oracle_opt_create.restype = C.c_void_p
         L.oracle_opt_create.argtypes = [dp]
         L.oracle_opt_destroy.restype = None
@@ -90,6 +141,7 @@ def lib() -> C.CDLL:
         L.oracle_closed_loop.restype = C.c_int
         L.oracle_closed_loop.argtypes = [dp, C.c_int64, C.c_int64, dp, dp, dp, dp, dp, C.POINTER(C.c_int64),
                                          C.POINTER(C.c_int64), C.c_int]
+    if full:
         L.oracle_dp_dynamics.restype = None
         L.oracle_dp_dynamics.argtypes = [dp, dp, C.c_double, dp, dp, dp]
         L.oracle_dp_rk4.restype = None
@@ -98,8 +150,7 @@ def lib() -> C.CDLL:
         L.oracle_dp_rk4_jac.argtypes = [dp, dp, C.c_double, C.c_double, dp, dp, dp]
         L.oracle_dp_batch_step.restype = C.c_int
         L.oracle_dp_batch_step.argtypes = L.oracle_batch_step.argtypes
-        _lib = L
-    return _lib
+    return L
 
 
 def _p(a):

@@ -87,6 +87,55 @@ def test_per_instance_weights_match_golden():
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# fixtures produced by the COMPILED REFERENCE (oracle/_ref/libref.so: the reference's own translation units on the
+# Eigen-interface shim; tests/golden/make_golden_ref.py).  These pin the CUDA path to the reference's sources, not
+# only to the restatement.
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["ref_config1_default.npz", "ref_config1_test_variant.npz", "ref_scratch_py.npz"])
+def test_single_solve_matches_compiled_reference(name):
+    g = load_golden(name)
+    s = _solver(1, **_overrides_from_opt(g["opt"]))
+    s.enable_iteration_log(True)
+    out = s.step(g["states"], g["dyn"], g["set_points"])
+    assert out.stats["termination_state"][0] == int(g["stats"][0, 0])
+    assert out.stats["n_iterations"][0] == int(g["stats"][0, 1])
+    assert out.stats["n_line_search_steps"][0] == int(g["stats"][0, 2])
+    assert _rel_cost(out, g["stats"])[0] <= REL_COST_TOL
+    assert np.allclose(out.u, g["u"], rtol=1e-7, atol=1e-7)
+    assert np.allclose(out.predicted_states, g["predicted"], rtol=1e-7, atol=1e-7)
+    log = s.get_iteration_log()[0]
+    assert np.allclose(log[0, 2:7], g["iter_log"][0, 0, 2:7], rtol=1e-11, atol=1e-11)
+    n = int(g["stats"][0, 1])
+    assert np.array_equal(log[:n, 7:9], g["iter_log"][0, :n, 7:9])
+
+
+@pytest.mark.parametrize("name,min_frac", [("ref_config2_256.npz", 0.95), ("ref_config2_testvariant_128.npz", 0.95),
+                                           ("ref_sweep_64.npz", 0.93), ("ref_config4_w160_24.npz", 0.85)])
+def test_batches_match_compiled_reference(name, min_frac):
+    g = load_golden(name)
+    B = g["states"].shape[0]
+    w = g["weights"] if g["weights"].size else None
+    out = _solver(B, **_overrides_from_opt(g["opt"])).step(g["states"], g["dyn"], g["set_points"], weights=w)
+    _check_batch(out, g["stats"], g["u"], min_frac=min_frac)
+
+
+def test_closed_loop_matches_compiled_reference():
+    """8 plants x 60 warm-started control ticks at the defaults, run by the compiled reference's Optimization +
+    Simulator, against the device-resident closed loop."""
+    g = load_golden("ref_closed_loop_8x60.npz")
+    B, T = g["x0"].shape[0], g["controls"].shape[1]
+    s = _solver(B)
+    fin, ctl, counts = s.closed_loop(T, g["x0"], g["dyn"], g["set_points"])
+    assert counts[0] == B * T == g["counts"][0]
+    close = np.abs(ctl - g["controls"]).max(axis=1) <= 1e-5 * np.maximum(np.abs(g["controls"]).max(axis=1), 1.0)
+    assert close.mean() >= 0.75, close.mean()
+    assert np.allclose(fin[close], g["final_state"][close], rtol=1e-5, atol=1e-6)
+    # the first control tick is a cold solve from identical inputs: every plant agrees
+    assert np.allclose(ctl[:, 0], g["controls"][:, 0], rtol=1e-6, atol=1e-6)
+    assert abs(int(counts[1]) - int(g["counts"][1])) <= 0.05 * g["counts"][1]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # seeded batches against the oracle
 # ----------------------------------------------------------------------------------------------------------------------
 # (OptimizationParams overrides, minimum fraction within 1e-8 relative cost).  The reference's own configurations
