@@ -1,4 +1,6 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see sqp.hpp header).  PARITY UNPINNED for controls/cost/iterations.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see sqp.hpp header).  Pinned against the reference's compiled sources
+// (oracle/_ref/libref.so): dynamics, RK4, RK4 Jacobians and the simulator are BIT-EQUAL to
+// single_pendulum_dynamics.hpp / integration.hpp / simulator.cc (tests/test_reference_pinning.py).
 //
 // CPU restatement of the cart-pole side of the reference hot path:
 //   dynamics + Jacobians     optimization/single_pendulum_dynamics.hpp:13-186

@@ -1,9 +1,10 @@
 """Generates tests/golden/*.npz from the CPU oracle (oracle/).
 
 The reference's own tests pin no control/cost/iteration vectors for Optimization::Step (the dump in
-optimization_test.cc:68-76 is compiled out) and the reference cannot be built here (Eigen absent), so these
-fixtures are frozen outputs of the oracle restatement: PARITY UNPINNED with respect to the reference binary, pinned
-with respect to the oracle.  Re-run only when the oracle is intentionally changed:
+optimization_test.cc:68-76 is compiled out).  These fixtures are frozen outputs of the oracle RESTATEMENT; the
+fixtures produced by the reference's own compiled sources are tests/golden/ref_*.npz (make_golden_ref.py), and
+tests/test_reference_pinning.py ties the two together.  The double-pendulum fixture (config 5) has no reference
+implementation at all: PARITY UNPINNED for it.  Re-run only when the oracle is intentionally changed:
 
     python tests/golden/make_golden.py
 """
