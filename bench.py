@@ -584,12 +584,17 @@ def main():
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    # every rank samples its own GPU: a slow or throttled GPU decides the max-over-ranks time
+    sampler.start()
     launches0 = launch_count()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     t_wall0 = time.perf_counter()
+    # Give the host a few ms of head start (untimed device work) so that a descheduled Python thread cannot leave the
+    # GPU idle between a step's start event and its kernel: with 8 ranks on a 16-core host that inflated one rank's
+    # per-step time by 40 % although every kernel took the same 0.81 ms.
+    for _ in range(32):
+        flush.fill_(0)
     for i in range(args.steps):
         flush.fill_(i & 0xFF)  # L2 flush between timed iterations (not timed)
         starts[i].record()
@@ -603,7 +608,7 @@ def main():
     launches = launch_count() - launches0
     step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, stops)])
     total_ms = float(step_ms.sum())
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
 
     stats = np.frombuffer(stats_d.cpu().numpy().tobytes(), dtype=_capi.STATS_DTYPE)
     n_iter_sum = float(stats["n_iterations"].sum())
@@ -661,7 +666,25 @@ def main():
                                     "note": "CPMPC_FLAG_LOW_LATENCY: two lanes per shooting segment"}}
 
     # ---- reduce over ranks: max time, summed work -----------------------------------------------------------------
+    per_rank = None
     if dist is not None:
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        mask = sum(1 << i for i, nm in enumerate(names) if nm in clocks["reasons"])
+        lm_iters = float(((stats["lambda"] > 0) | (stats["n_failed_line_searches"] > 0)).sum())
+        mine = torch.tensor([total_ms / args.steps, float(np.median(step_ms)), float(step_ms.max()),
+                             clocks["sm_mhz"] or 0.0, float(mask), float(stats["n_line_search_steps"].max()), lm_iters],
+                            dtype=torch.float64, device=dev)
+        allr = torch.empty((world, 7), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr, mine)
+        per_rank = {"mean_step_ms": [float(v) for v in allr[:, 0]], "median_step_ms": [float(v) for v in allr[:, 1]],
+                    "max_step_ms": [float(v) for v in allr[:, 2]], "sm_mhz": [float(v) for v in allr[:, 3]],
+                    "throttle_reasons": [[nm for i, nm in enumerate(names) if int(v) >> i & 1] for v in allr[:, 4]],
+                    "max_merit_evaluations_of_one_instance": [int(v) for v in allr[:, 5]],
+                    "instances_with_failed_line_search_or_lm_damping": [int(v) for v in allr[:, 6]],
+                    "note": "each rank owns different instances and 4096 instances are ONE wave of warps, so a "
+                            "rank's step time is the latency of its hardest warp; the max over ranks is reported"}
+        all_reasons = sorted({r for rs in per_rank["throttle_reasons"] for r in rs})
+        clocks = dict(clocks, reasons=all_reasons, sm_mhz_min_over_ranks=min(per_rank["sm_mhz"]))
         t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_s = float(t[0]), float(t[1])
@@ -717,6 +740,8 @@ def main():
         "aggregate_algorithmic_tflops": flops_step_all / (kernel_ms * 1e-3) / 1e12,
     }
 
+    if per_rank is not None:
+        line["per_rank"] = per_rank
     if not args.no_cpu_baseline and world == 1:
         res, best, kind = cpu_baseline(states_h, dyn_h, sp_h, repeats=3)
         line["cpu_baseline"] = {"value": B / best, "unit": UNIT, "cores": res.threads, "kind": kind,
