@@ -49,6 +49,23 @@ def algorithmic_flops(n_iter, n_ls, W=40, S=10, n_te=3, n_cost=81, nx=4, C_f=76,
     return n_iter * (F_lin + F_qp + F_dir) + n_ls * F_merit + 2 * F_roll
 
 
+NCU_SUMMARY = "profiles/r01_h_workqueue.json"
+
+
+def ncu_dram_traffic(batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the solve kernel from the committed ncu summary (captured at
+    batch 4096); None for any other batch or when the summary is missing."""
+    if batch != 4096:
+        return None
+    try:
+        with open(os.path.join(ROOT, NCU_SUMMARY)) as fh:
+            raw = json.load(fh)["raw"]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        return sum(float(raw[k]["value"]) * scale[raw[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def hbm_bytes_per_solve(W=40, S=10):
     """Algorithmic HBM traffic of one solve: inputs + warm start in, results + new warm start out."""
     NS = W // S + 1
@@ -726,7 +743,11 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
-                     "frac": achieved_tflops / peak_tflops if peak_tflops else None, "traffic": None,
+                     "frac": achieved_tflops / peak_tflops if peak_tflops else None,
+                     "traffic": ncu_dram_traffic(B), "traffic_unit": "bytes of DRAM read+write per launch",
+                     "traffic_source": NCU_SUMMARY + " (one `ncu --set full` capture of this kernel at this batch; "
+                                       "algorithmic HBM bytes per launch = batch x hbm_bytes_per_solve = "
+                                       f"{B * hbm_bytes_per_solve(W, S)}: outputs stay in the 126 MB L2)",
                      "peak_source": "DFMA microkernel measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                      "flops_model": "SURVEY.md 8(d) algorithmic count from the solver's own n_iter / n_ls counters",
                      "flops_per_solve": flops_step / B,

@@ -32,8 +32,13 @@ def sass_rows(rep):
 def line_map(lib, mangled_sub):
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
-    cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+    txt = ""
+    for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+        # the library holds one cubin per translation unit: take the one that defines the kernel
+        cand = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+        if any(l.startswith("//---") and ".text." in l and mangled_sub in l for l in cand.splitlines()):
+            txt = cand
+            break
     lines = txt.splitlines()
     out = []
     inside = False
