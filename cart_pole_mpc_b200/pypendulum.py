@@ -92,6 +92,74 @@ class OptimizationOutputs:
         return "\n".join(lines) + "\n"
 
 
+    # ---- the JSON log format of the reference's web front end --------------------------------------------------------
+    def to_dict(self) -> dict:
+        """Same object layout as nlohmann's `json(OptimizationOutputs)` in the reference: optimization/wasm.cc:19-27,46-65
+        (OptimizationOutputs, SingleCartPoleState) and dependencies/mini_opt/source/serialization.cc:32-134
+        (NLSSolverOutputs, NLSIteration, Errors, DirectionalDerivatives, LineSearchStep; enums by name).  The
+        equality-only problem always uses the null-space QP, so `qp_outputs` is the QPNullSpaceTerminationState name
+        and `qp_eigenvalues` is null (log_qp_eigenvalues is never enabled by Optimization)."""
+        def state(s):
+            return {"b_x": s.b_x, "th_1": s.th_1, "th_1_dot": s.th_1_dot, "b_x_dot": s.b_x_dot}
+
+        iterations = []
+        for i in range(int(self.stats["n_iterations"])):
+            r = self._iter_log[i]
+            iterations.append({
+                "iteration": i,
+                "optimizer_state": "NOMINAL" if int(r[0]) == 0 else "ATTEMPTING_RESTORE_LM",
+                "lambda": float(r[1]),
+                "errors_initial": {"f": float(r[2]), "equality": float(r[3])},
+                "qp_outputs": "SUCCESS",
+                "qp_eigenvalues": None,
+                "directional_derivatives": {"d_f": float(r[4]), "d_equality": float(r[5])},
+                "penalty": float(r[6]),
+                "step_result": _b.STEP_RESULT_NAMES.get(int(r[7]), "?"),
+                "line_search_steps": [
+                    {"alpha": float(r[9 + 3 * k]), "errors": {"f": float(r[10 + 3 * k]), "equality": float(r[11 + 3 * k])}}
+                    for k in range(min(int(r[8]), 6))],
+            })
+        return {
+            "initial_state": state(self.initial_state),
+            "previous_solution": [float(v) for v in self.previous_solution],
+            "solver_outputs": {"termination_state": _b.TERMINATION_NAMES.get(int(self.stats["termination_state"]), "?"),
+                               "iterations": iterations},
+            "u": [float(v) for v in self.u],
+            "predicted_states": [state(s) for s in self.predicted_states],
+        }
+
+    def to_json(self, **dumps_kwargs) -> str:
+        import json
+        return json.dumps(self.to_dict(), **dumps_kwargs)
+
+
+def outputs_from_json(text) -> "OptimizationOutputs":
+    """Inverse of OptimizationOutputs.to_json (optimization/wasm.cc:48-56 `from_json`): rebuilds an outputs object from
+    a log written by either implementation, e.g. to replay it through solver_summary()."""
+    import json
+    j = json.loads(text) if isinstance(text, (str, bytes)) else text
+    term_ids = {v: k for k, v in _b.TERMINATION_NAMES.items()}
+    step_ids = {v: k for k, v in _b.STEP_RESULT_NAMES.items()}
+    its = j["solver_outputs"]["iterations"]
+    log = np.zeros((max(len(its), 1), 27))
+    n_ls = n_failed = 0
+    for i, it in enumerate(its):
+        steps = it["line_search_steps"]
+        log[i, :9] = [0.0 if it["optimizer_state"] == "NOMINAL" else 1.0, it["lambda"], it["errors_initial"]["f"],
+                      it["errors_initial"]["equality"], it["directional_derivatives"]["d_f"],
+                      it["directional_derivatives"]["d_equality"], it["penalty"], step_ids[it["step_result"]],
+                      len(steps)]
+        for k, st in enumerate(steps[:6]):
+            log[i, 9 + 3 * k:12 + 3 * k] = [st["alpha"], st["errors"]["f"], st["errors"]["equality"]]
+        n_ls += len(steps)
+        n_failed += it["step_result"] not in ("SUCCESS", "FIRST_ORDER_SATISFIED")
+    stats = {"termination_state": term_ids[j["solver_outputs"]["termination_state"]], "n_iterations": len(its),
+             "n_line_search_steps": n_ls, "n_failed_line_searches": n_failed}
+    mk = lambda d: SingleCartPoleState(d["b_x"], d["th_1"], d["b_x_dot"], d["th_1_dot"])
+    return OptimizationOutputs(mk(j["initial_state"]), list(j["previous_solution"]), list(j["u"]),
+                               [mk(d) for d in j["predicted_states"]], stats, log)
+
+
 class Optimization:
     """wrapper.cc:87-90 / optimization/optimization.hpp:73-108 — a GPU batch of one."""
 

@@ -197,3 +197,37 @@ def test_cpp_facade_compiles_against_the_c_abi(cuda_lib, tmp_path):
     if not torch.cuda.is_available():
         proc = subprocess.run([str(exe)], capture_output=True, text=True)
         assert proc.returncode != 0 and "FACADE_CLOSED_LOOP_OK" not in proc.stdout
+
+
+def test_json_log_format_matches_the_reference_schema_and_round_trips():
+    """The web front end's log format (optimization/wasm.cc:19-27,46-65; mini_opt/source/serialization.cc:32-134):
+    key names, enum names and nesting, written from a solver log of the COMPILED REFERENCE (golden fixture), read
+    back, and rendered by the ToString-style summary."""
+    import json
+    import numpy as np
+    from conftest import load_golden
+    from cart_pole_mpc_b200 import pypendulum as pp
+    g = load_golden("ref_config1_default.npz")
+    st = g["stats"][0]
+    stats = {"termination_state": int(st[0]), "n_iterations": int(st[1]), "n_line_search_steps": int(st[2])}
+    out = pp.OptimizationOutputs(pp.SingleCartPoleState(*g["states"][0]), [], g["u"][0].tolist(),
+                                 [pp.SingleCartPoleState(*r) for r in g["predicted"][0]], stats, g["iter_log"][0])
+    j = json.loads(out.to_json())
+    assert list(j) == ["initial_state", "previous_solution", "solver_outputs", "u", "predicted_states"]
+    assert set(j["initial_state"]) == {"b_x", "th_1", "th_1_dot", "b_x_dot"}
+    assert j["solver_outputs"]["termination_state"] == "MAX_ITERATIONS"
+    its = j["solver_outputs"]["iterations"]
+    assert len(its) == 8 and len(j["u"]) == 40 and len(j["predicted_states"]) == 40
+    assert list(its[0]) == ["iteration", "optimizer_state", "lambda", "errors_initial", "qp_outputs", "qp_eigenvalues",
+                            "directional_derivatives", "penalty", "step_result", "line_search_steps"]
+    assert its[0]["optimizer_state"] == "NOMINAL" and its[0]["qp_outputs"] == "SUCCESS" and its[0]["qp_eigenvalues"] is None
+    assert set(its[0]["errors_initial"]) == {"f", "equality"}
+    assert set(its[0]["directional_derivatives"]) == {"d_f", "d_equality"}
+    assert set(its[0]["line_search_steps"][0]) == {"alpha", "errors"} and its[0]["line_search_steps"][0]["alpha"] == 1.0
+    assert sum(len(it["line_search_steps"]) for it in its) == int(st[2])
+    # doubles survive the text round trip bit for bit (repr round-trips IEEE doubles), and so does the summary
+    back = pp.outputs_from_json(out.to_json())
+    assert back.to_dict() == out.to_dict()
+    assert back.solver_summary() == out.solver_summary()
+    assert np.array_equal(np.array(back.u), g["u"][0])
+    assert "termination = MAX_ITERATIONS" in back.solver_summary()
