@@ -591,7 +591,9 @@ __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights<PL::NX>& 
     }
     GP_GSYNC();
 
-    // (iii) eliminate the S controls (right-looking LDL^T, one trailing column per lane)
+    // (iii) eliminate the S controls.  Same two bit-identical forms as solver_kernel.cuh: right-looking for wide lane
+    // groups, left-looking (register accumulation, phase A control columns / phase B trailing block) for L <= 4.
+    if constexpr (L >= 8) {
     if (c.gl == 0) {
       const double piv = aug[0];
       invd[0] = (piv > 0.0) ? fm::rcp(piv) : -1.0;
@@ -614,6 +616,64 @@ __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights<PL::NX>& 
           axpy_neg(colc + cc + 1, colj + cc + 1, l, D - cc - 1);
         } else {
           axpy_neg(colc + cc, colj + cc, l, D - cc);
+        }
+      }
+      GP_GSYNC();
+    }
+    } else {
+      constexpr int R = 4;  // rows per register chunk
+      for (int j = 0; j < S; ++j) {
+        const int cbj = cbase(D, j);
+        for (int r0 = j + R * c.gl; r0 < D; r0 += R * L) {
+          int rr[R];
+          double y[R];
+#pragma unroll
+          for (int t = 0; t < R; ++t) {
+            rr[t] = min(r0 + t, D - 1);
+            y[t] = aug[cbj + rr[t]];
+          }
+          int cb = 0;
+          for (int i = 0; i < j; ++i) {
+            const double* ci = aug + cb;  // column i: entry (r, i) at ci[r]
+            const double l = ci[j] * invd[i];
+#pragma unroll
+            for (int t = 0; t < R; ++t) y[t] = fma(-l, ci[rr[t]], y[t]);
+            cb += D - i - 1;
+          }
+#pragma unroll
+          for (int t = 0; t < R; ++t)
+            if (r0 + t < D) aug[cbj + r0 + t] = y[t];
+          if (r0 == j) invd[j] = (y[0] > 0.0) ? fm::rcp(y[0]) : -1.0;
+        }
+        GP_GSYNC();
+        if (!(invd[j] > 0.0)) {
+          ok = false;
+          break;
+        }
+      }
+      if (ok) {
+        for (int cc = S + c.gl; cc < D; cc += L) {
+          const int cbc = cbase(D, cc);
+          for (int r0 = cc; r0 < D; r0 += R) {
+            int rr[R];
+            double y[R];
+#pragma unroll
+            for (int t = 0; t < R; ++t) {
+              rr[t] = min(r0 + t, D - 1);
+              y[t] = aug[cbc + rr[t]];
+            }
+            int cb = 0;
+            for (int i = 0; i < S; ++i) {
+              const double* ci = aug + cb;
+              const double l = ci[cc] * invd[i];
+#pragma unroll
+              for (int t = 0; t < R; ++t) y[t] = fma(-l, ci[rr[t]], y[t]);
+              cb += D - i - 1;
+            }
+#pragma unroll
+            for (int t = 0; t < R; ++t)
+              if (r0 + t < D) aug[cbc + r0 + t] = y[t];
+          }
         }
       }
       GP_GSYNC();

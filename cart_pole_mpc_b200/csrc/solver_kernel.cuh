@@ -423,6 +423,12 @@ __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights& w, const
     }
     CPMPC_GSYNC();
 
+    // Two implementations of the same elimination, bit-identical in their results (profiles/ab_compare.py).  Wide
+    // lane groups (L >= 8: long horizons, one column per lane, several warps per scheduler) are instruction-bound and
+    // keep the right-looking form; narrow groups (L <= 4: the default horizon, Levenberg-Marquardt iterations only,
+    // one warp per scheduler) are latency-bound and use the left-looking form below, 5-8 % faster end to end on
+    // LM-heavy batches.
+    if constexpr (L >= 8) {
     // (iii) eliminate the S controls: right-looking LDL^T steps over the whole D x D matrix, one trailing column per
     // lane.  The lane that owns column j + 1 handles it first and publishes the reciprocal of the next pivot.
     if (c.gl == 0) {
@@ -451,6 +457,73 @@ __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights& w, const
         }
       }
       CPMPC_GSYNC();
+    }
+    } else {
+    // (iii) eliminate the S controls: LEFT-looking LDL^T.  Every entry (r, c) of the factor / Schur complement is
+    //   a(r, c) - sum_{i < min(c, S)} (a(c, i) / d_i) a(r, i),   accumulated in increasing i with one FMA per term
+    // - exactly the updates, in exactly the order, that a right-looking elimination applies to that entry (so the
+    // result is bit-identical to it) - but the running value stays in a register instead of making a shared-memory
+    // round trip per elimination step, and the loads of a chain do not depend on each other.  Phase A finalises the
+    // control columns one after the other (rows split across the lanes, one barrier per column, the pivot reciprocal
+    // published with it); phase B then updates the trailing (xi, rho) block, one column per lane, without barriers.
+    {
+      constexpr int R = 4;  // rows per register chunk
+      for (int j = 0; j < S; ++j) {
+        const int cbj = cbase(D, j);
+        for (int r0 = j + R * c.gl; r0 < D; r0 += R * L) {
+          int rr[R];
+          double y[R];
+#pragma unroll
+          for (int t = 0; t < R; ++t) {
+            rr[t] = min(r0 + t, D - 1);
+            y[t] = aug[cbj + rr[t]];
+          }
+          int cb = 0;
+          for (int i = 0; i < j; ++i) {
+            const double* ci = aug + cb;  // column i: entry (r, i) at ci[r]
+            const double l = ci[j] * invd[i];
+#pragma unroll
+            for (int t = 0; t < R; ++t) y[t] = fma(-l, ci[rr[t]], y[t]);
+            cb += D - i - 1;
+          }
+#pragma unroll
+          for (int t = 0; t < R; ++t)
+            if (r0 + t < D) aug[cbj + r0 + t] = y[t];
+          if (r0 == j) invd[j] = (y[0] > 0.0) ? fm::rcp(y[0]) : -1.0;
+        }
+        CPMPC_GSYNC();
+        if (!(invd[j] > 0.0)) {
+          ok = false;
+          break;
+        }
+      }
+      if (ok) {
+        for (int cc = S + c.gl; cc < D; cc += L) {
+          const int cbc = cbase(D, cc);
+          for (int r0 = cc; r0 < D; r0 += R) {
+            int rr[R];
+            double y[R];
+#pragma unroll
+            for (int t = 0; t < R; ++t) {
+              rr[t] = min(r0 + t, D - 1);
+              y[t] = aug[cbc + rr[t]];
+            }
+            int cb = 0;
+            for (int i = 0; i < S; ++i) {
+              const double* ci = aug + cb;
+              const double l = ci[cc] * invd[i];
+#pragma unroll
+              for (int t = 0; t < R; ++t) y[t] = fma(-l, ci[rr[t]], y[t]);
+              cb += D - i - 1;
+            }
+#pragma unroll
+            for (int t = 0; t < R; ++t)
+              if (r0 + t < D) aug[cbc + r0 + t] = y[t];
+          }
+        }
+      }
+      CPMPC_GSYNC();
+    }
     }
     if (!ok) break;
 
