@@ -680,21 +680,46 @@ __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights<PL::NX>& 
     }
     if (!ok) break;
 
-    // (iv) gains by back-substitution, spilled to the group's global scratch
-    for (int q = c.gl; q < n2; q += L) {
-      const int rq = S + q;
-      double* dst = c.kk + ((size_t)s * NCOL + q) * S;
-      double nxt = aug[cbase(D, S - 1) + rq];
-      for (int j = S - 1; j >= 0; --j) {
-        const double xj = nxt * invd[j];
-        __stcg(dst + j, xj);
-        if (j == 0) break;
-        const double* pi = aug + cbase(D, j - 1);
-        nxt = fma(-pi[j], xj, pi[rq]);
-        int o = cbase(D, j - 1);
-        for (int i = j - 2; i >= 0; --i) {
-          o -= (D - i - 1);
-          aug[o + rq] = fma(-aug[o + j], xj, aug[o + rq]);
+    // (iv) gains: row S + q of the panel holds Z[:, q]; x_i = rd_i (z_i - sum_{j > i} a(j, i) x_j).
+    {
+      // Left-looking form: the sum of one unknown is accumulated in a register in the order j = S-1 .. i+1 (the order
+      // in which a right-looking sweep applies the same FMAs to z_i: bit-identical to the first implementation,
+      // profiles/ab_compare.py); solved unknowns are parked in the dead z slots of their columns, the latest one stays
+      // in a register, and two right-hand sides are interleaved per lane for instruction-level parallelism.
+      for (int q0 = c.gl; q0 < n2; q0 += 2 * L) {
+        const int q1 = q0 + L;
+        const bool two = q1 < n2;
+        const int ra = S + q0, rb = two ? S + q1 : ra;
+        double* dsta = c.kk + ((size_t)s * NCOL + q0) * S;
+        double* dstb = c.kk + ((size_t)s * NCOL + (two ? q1 : q0)) * S;
+        double xa = 0.0, xb = 0.0;
+        int cbi = cbase(D, S - 1);
+        const int cb_last = cbi;
+        for (int i = S - 1; i >= 0; --i) {
+          double* ci = aug + cbi;  // column i: a(j, i) at ci[j]
+          double acca = ci[ra], accb = ci[rb];
+          int ob = cb_last;  // column j = S-1
+          for (int j = S - 1; j > i + 1; --j) {
+            const double a = ci[j];
+            acca = fma(-a, aug[ob + ra], acca);
+            accb = fma(-a, aug[ob + rb], accb);
+            ob -= (D - j);  // cbase(D, j - 1)
+          }
+          if (i < S - 1) {
+            const double a = ci[i + 1];
+            acca = fma(-a, xa, acca);
+            accb = fma(-a, xb, accb);
+          }
+          const double rd = invd[i];
+          xa = acca * rd;
+          xb = accb * rd;
+          __stcg(dsta + i, xa);
+          ci[ra] = xa;
+          if (two) {
+            __stcg(dstb + i, xb);
+            ci[rb] = xb;
+          }
+          cbi -= (D - i);  // cbase(D, i - 1)
         }
       }
     }
