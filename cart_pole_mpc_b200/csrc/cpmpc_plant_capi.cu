@@ -101,8 +101,11 @@ void BuildLayout(gp::GpCfg& k, int nx, int nc) {
   k.off_gam = take(nx * W > n_cand ? nx * W : n_cand);
   k.off_xc = k.off_gam;
   k.off_uc = k.off_xc + nx * NS;
+  // Riccati stage matrix (packed lower triangle) or, aliased, the condensed-QP scratch Z [nx][W], tl [W], tinv [W]
   const int D = S + ncol;
-  k.off_aug = take(D * (D + 1) / 2);
+  const int n_ric = D * (D + 1) / 2;
+  const int n_cond = k.condensed ? (nx + 2) * W : 0;
+  k.off_aug = take(n_ric > n_cond ? n_ric : n_cond);
   k.off_vbuf = take(xi * xi + xi * nrm);
   k.off_invd = take(S);
   k.off_dyn = take(nc);
@@ -241,6 +244,14 @@ int cpmpc_plant_create(int plant, const cpmpc_plant_params* params, int64_t batc
   if (const char* env = std::getenv("CPMPC_PLANT_LANES")) {
     const int v = std::atoi(env);
     if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) lanes = v;
+  }
+  // QP method for the undamped iterations: condensed while the horizon is short enough for open-loop sensitivity
+  // products to stay accurate, Riccati beyond (and always for Levenberg-Marquardt iterations); same rule and the same
+  // CPMPC_QP override as the single-pendulum handle (cpmpc_capi.cu)
+  k.condensed = (k.W * k.dt <= 0.6) ? 1 : 0;
+  if (const char* env = std::getenv("CPMPC_QP")) {
+    if (std::strcmp(env, "riccati") == 0) k.condensed = 0;
+    if (std::strcmp(env, "condensed") == 0) k.condensed = 1;
   }
   BuildLayout(k, nx, PlantNc(plant));
   size_t smem_per_warp = 0;

@@ -10,7 +10,7 @@
 //   variable layout [x(0) .. x(NS-1) | u(0) .. u(W-1)], costs (u, u-rate, u_0 - u_prev, terminal), terminal rule
 //   (negative weight = hard equality), initial-state equalities, shooting defects with angle wrapping, retraction with
 //   angle wrapping and clamps, warm start by shifting the controls, FillInitialGuess, ComputePredictedStates.
-// What is not here (solver_kernel.cuh only): the condensed QP, chunked linearisation, the fused closed loop.
+// What is not here (solver_kernel.cuh only): chunked linearisation, the fused closed loop.
 //
 // A Plant provides
 //   NX, NQ = NX/2 (x = [q, q'], so rows 0..NQ-1 of the state Jacobian are [0 I]), NP (doubles of parameters per
@@ -218,6 +218,7 @@ constexpr int GP_MAX_NX = 6;
 
 struct GpCfg {
   int W, S, NS, nseg, N, max_iter, max_ls;
+  int condensed;  // 1: lambda == 0 iterations use the condensed QP (short horizons), 0: always Riccati
   int stride;
   int off_xs, off_u, off_dxs, off_du, off_phi, off_e, off_gam, off_aug, off_vbuf, off_invd, off_dyn, off_xc, off_uc;
   int kk_stride;
@@ -839,6 +840,265 @@ __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights<PL::NX>& 
 #undef GP_TRS
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same QP in condensed form for undamped iterations on short horizons (cfg.condensed), NX-generic version of
+// condensed_qp in solver_kernel.cuh: with the shooting states eliminated forward through the linearised dynamics the
+// Hessian over the W controls is T + U^T D U, T the tridiagonal control / control-rate Hessian (factored once per
+// solve) and U the NX rows of terminal-state sensitivities (soft rows carry weight d = w^2, hard rows are
+// constraints).  With Z = L^-1 U^T the multipliers come from an NX x NX system and du from one more bidiagonal solve.
+// Scratch (aliases the Riccati stage matrix): Z [NX][W], tl [W], tinv [W].
+// ---------------------------------------------------------------------------------------------------------------------
+template <int L, class PL>
+__device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights<PL::NX>& w, bool& tri_valid,
+                                             const double (&x_cur)[PL::NX], const double set_point, double& cdx) {
+  constexpr int NX = PL::NX;
+  constexpr int NP = NX * (NX + 1) / 2;  // Gram pairs (i <= j), then NX gradient entries
+  const GpCfg& k = *c.cfg;
+  const int W = k.W, S = k.S, NS = k.NS, nseg = k.nseg;
+  const double* xs = c.sm + k.off_xs;
+  double* dxs = c.sm + k.off_dxs;
+  double* du = c.sm + k.off_du;
+  const double* Phi = c.sm + k.off_phi;
+  const double* ev = c.sm + k.off_e;
+  const double* Gam = c.sm + k.off_gam;
+  double* Z = c.sm + k.off_aug;  // [NX][W]
+  double* tl = Z + NX * W;       // sub-diagonal multipliers of the unit bidiagonal factor
+  double* tinv = tl + W;         // reciprocal pivots
+  const double wu2 = w.w_u * w.w_u, wr2 = w.w_r * w.w_r;
+  bool ok = true;
+
+  // (1) factor T once per solve (lane L-1, while the other lanes build the rows of U)
+  if (!tri_valid && c.gl == L - 1) {
+    double dprev_inv = 0.0;
+    for (int j = 0; j < W; ++j) {
+      const double a = wu2 + wr2 * ((j + 1 < W) ? 2.0 : 1.0);
+      double l = 0.0, d = a;
+      if (j > 0) {
+        l = -wr2 * dprev_inv;
+        d = fma(l, wr2, a);
+      }
+      ok = ok && (d > 0.0);
+      dprev_inv = fm::rcp(d);
+      tl[j] = l;
+      tinv[j] = dprev_inv;
+    }
+  }
+  tri_valid = true;
+  // (2) rows of U: sensitivity of the terminal node to every control, through the later segments
+  for (int col = c.gl; col < W; col += L) {
+    const int s = col / S;
+    double v[NX];
+#pragma unroll
+    for (int a = 0; a < NX; ++a) v[a] = Gam[a * W + col];
+    for (int t = s + 1; t < nseg; ++t) {
+      const double* Ph = Phi + NX * NX * t;
+      double n[NX];
+#pragma unroll
+      for (int r = 0; r < NX; ++r) {
+        double acc = Ph[NX * r] * v[0];
+#pragma unroll
+        for (int q = 1; q < NX; ++q) acc += Ph[NX * r + q] * v[q];
+        n[r] = acc;
+      }
+#pragma unroll
+      for (int r = 0; r < NX; ++r) v[r] = n[r];
+    }
+#pragma unroll
+    for (int a = 0; a < NX; ++a) Z[a * W + col] = v[a];
+  }
+  // node steps for du = 0: m_0 = -(x_0 - x_cur), m_{s+1} = Phi_s m_s + e_s (every lane, registers)
+  double m[NX], m0[NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+    double d = xs[i] - x_cur[i];
+    if (PL::is_angle(i)) d = mod_pi(d);
+    m[i] = -d;
+    m0[i] = -d;
+  }
+  for (int s = 0; s < nseg; ++s) {
+    const double* Ph = Phi + NX * NX * s;
+    double n[NX];
+#pragma unroll
+    for (int r = 0; r < NX; ++r) {
+      double acc = Ph[NX * r] * m[0];
+#pragma unroll
+      for (int q = 1; q < NX; ++q) acc += Ph[NX * r + q] * m[q];
+      n[r] = acc + ev[NX * s + r];
+    }
+#pragma unroll
+    for (int r = 0; r < NX; ++r) m[r] = n[r];
+  }
+  GP_GSYNC();
+  ok = __all_sync(c.gmask, ok);
+  if (!ok) return false;
+
+  // (3) forward substitution with the unit bidiagonal factor: the NX rows of Z and the gradient (in du[]), one
+  // right-hand side per lane, the running value carried in a register
+  for (int r = c.gl; r < NX + 1; r += L) {
+    double* row = (r < NX) ? (Z + r * W) : du;
+    double prev = row[0];
+    for (int j = 1; j < W; ++j) {
+      prev = fma(-tl[j], prev, row[j]);
+      row[j] = prev;
+    }
+  }
+  GP_GSYNC();
+
+  // (4) Gram entries sum_q Z_i[q] Z_j[q] / d_q (i <= j) and sum_q Z_i[q] g[q] / d_q: every lane accumulates over its
+  // own columns, a group sum finishes each entry (all lanes need all of them)
+  double gm[NP + NX];
+#pragma unroll
+  for (int e = 0; e < NP + NX; ++e) gm[e] = 0.0;
+  for (int q = c.gl; q < W; q += L) {
+    const double ti = tinv[q];
+    const double zg = du[q];
+    double z[NX], sc[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      z[i] = Z[i * W + q];
+      sc[i] = z[i] * ti;
+    }
+    int e = 0;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+#pragma unroll
+      for (int j = i; j < NX; ++j) {
+        gm[e] = fma(sc[i], z[j], gm[e]);
+        ++e;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) gm[NP + i] = fma(sc[i], zg, gm[NP + i]);
+  }
+#pragma unroll
+  for (int e = 0; e < NP + NX; ++e) gm[e] = group_sum<L>(gm[e], c.gmask);
+
+  // (5) NX x NX system for the row multipliers, every lane redundantly in registers
+  double A[NX][NX];
+  {
+    int e = 0;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+#pragma unroll
+      for (int j = i; j < NX; ++j) {
+        A[i][j] = gm[e];
+        A[j][i] = gm[e];
+        ++e;
+      }
+    }
+  }
+  double sig[NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+    double d = xs[NX * (NS - 1) + i] - target_of<PL>(i, set_point);
+    if (PL::is_angle(i)) d = mod_pi(d);
+    double invd, off;
+    if (w.wt[i] < 0.0) {
+      invd = 0.0;  // hard row
+      off = m[i] + d;
+    } else {
+      const double dd = w.wt[i] * w.wt[i];
+      if (dd > 0.0) {
+        invd = 1.0 / dd;
+        off = m[i] + d;
+      } else {
+        invd = -1.0;  // zero weight: the row does not exist
+        off = 0.0;
+      }
+    }
+    if (invd < 0.0) {
+#pragma unroll
+      for (int j = 0; j < NX; ++j) {
+        A[i][j] = 0.0;
+        A[j][i] = 0.0;
+      }
+      A[i][i] = 1.0;
+      sig[i] = 0.0;
+    } else {
+      A[i][i] += invd;
+      sig[i] = off - gm[NP + i];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NX; ++j) {
+    double d = A[j][j];
+#pragma unroll
+    for (int q = 0; q < j; ++q) d -= A[j][q] * A[j][q];
+    if (!(d > 0.0)) ok = false;
+    const double inv = 1.0 / sqrt(d);
+    A[j][j] = inv;
+#pragma unroll
+    for (int i = j + 1; i < NX; ++i) {
+      double sacc = A[i][j];
+#pragma unroll
+      for (int q = 0; q < j; ++q) sacc -= A[i][q] * A[j][q];
+      A[i][j] = sacc * inv;
+    }
+  }
+  if (!ok) return false;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+    double sacc = sig[i];
+#pragma unroll
+    for (int q = 0; q < i; ++q) sacc -= A[i][q] * sig[q];
+    sig[i] = sacc * A[i][i];
+  }
+#pragma unroll
+  for (int i = NX - 1; i >= 0; --i) {
+    double sacc = sig[i];
+#pragma unroll
+    for (int q = i + 1; q < NX; ++q) sacc -= A[q][i] * sig[q];
+    sig[i] = sacc * A[i][i];
+  }
+
+  // (6) du = -L^-T D^-1 (z_g + Z sigma); c_u . du = -(L^-1 g)^T D^-1 (z_g + Z sigma)
+  double part = 0.0;
+  for (int q = c.gl; q < W; q += L) {
+    const double zg = du[q];
+    double acc = zg;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) acc += sig[i] * Z[i * W + q];
+    const double wq = acc * tinv[q];
+    part = fma(zg, wq, part);
+    du[q] = wq;
+  }
+  cdx = -part;  // this lane's share of c_u . du
+  GP_GSYNC();
+  if (c.gl == 0) {
+    double nxt = du[W - 1];
+    du[W - 1] = -nxt;
+    for (int j = W - 2; j >= 0; --j) {
+      nxt = fma(-tl[j + 1], nxt, du[j]);
+      du[j] = -nxt;
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) dxs[i] = m0[i];
+  }
+  GP_GSYNC();
+
+  // (7) node steps by forward propagation
+  double xi[NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) xi[i] = m0[i];
+  for (int s = 0; s < nseg; ++s) {
+    const double* Ph = Phi + NX * NX * s;
+    for (int a = c.gl; a < NX; a += L) {
+      double n0 = ev[NX * s + a];
+#pragma unroll
+      for (int q = 0; q < NX; ++q) n0 += Ph[NX * a + q] * xi[q];
+      const double* ga = Gam + a * W + s * S;
+      const double* vv = du + s * S;
+      double n1 = 0.0;
+      for (int j = 0; j < S; ++j) n1 = fma(ga[j], vv[j], n1);
+      dxs[NX * (s + 1) + a] = n0 + n1;
+    }
+    GP_GSYNC();
+#pragma unroll
+    for (int a = 0; a < NX; ++a) xi[a] = dxs[NX * (s + 1) + a];
+  }
+  return true;
+}
+
 struct SolveResult {
   int termination, n_iter, n_ls, n_failed, last_step_result, opt_state;
   double f, eq, penalty, lambda;
@@ -867,7 +1127,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
     double f0, eq0, d_f, d_eq, lambda_in;
     double alpha, a_prev, phi_prev, a_prev2, phi_prev2, step_f, step_eq, phi0, dphi0, linf;
     int opt_state, step_result, n_steps;
-    bool active, have_cur, ls_done;
+    bool active, have_cur, ls_done, tri_valid;
   } cold;
   asm volatile("" : : "l"(&cold) : "memory");
   bool& active = cold.active;
@@ -877,6 +1137,8 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
   double& cur_f = cold.cur_f;
   double& cur_eq = cold.cur_eq;
   bool& have_cur = cold.have_cur;
+  bool& tri_valid = cold.tri_valid;
+  tri_valid = false;  // factorisation of T (condensed QP) is cached across the iterations of one solve
   active = active_in;
   lambda = 0.0;
   penalty = k.pen_init;
@@ -889,6 +1151,23 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
   res.n_ls = 0;
   res.n_failed = 0;
   res.last_step_result = SR_SUCCESS;
+
+  // gradient of the control costs at the current controls into du[] (the QP routines consume and overwrite it)
+  auto fill_gradient = [&]() {
+    for (int col = c.gl; col < W; col += L) {
+      double g = 0.0;
+      const double uk = u[col];
+      if (w.w_r > 0.0) {
+        const double wr2 = w.w_r * w.w_r;
+        if (col + 1 < W) g += wr2 * (uk - u[col + 1]);
+        if (col > 0) g -= wr2 * (u[col - 1] - uk);
+        if (col == 0) g += wr2 * (uk - u_prev);
+      }
+      if (w.w_u > 0.0) g += (w.w_u * w.w_u) * uk;
+      du[col] = g;
+    }
+    GP_GSYNC();
+  };
 
   for (int iter = 0; iter < k.max_iter; ++iter) {
     if (!__any_sync(0xffffffffu, active)) break;
@@ -982,19 +1261,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
         have_cur = true;
       }
       // gradient of the control costs (optimization.cc:270-301), parked in du[]
-      for (int col = c.gl; col < W; col += L) {
-        double g = 0.0;
-        const double uk = u[col];
-        if (w.w_r > 0.0) {
-          const double wr2 = w.w_r * w.w_r;
-          if (col + 1 < W) g += wr2 * (uk - u[col + 1]);
-          if (col > 0) g -= wr2 * (u[col - 1] - uk);
-          if (col == 0) g += wr2 * (uk - u_prev);
-        }
-        if (w.w_u > 0.0) g += (w.w_u * w.w_u) * uk;
-        du[col] = g;
-      }
-      GP_GSYNC();
+      fill_gradient();
       if (!isfinite(f0) || !isfinite(eq0)) {
         res.termination = TS_REJECTED;  // the reference throws here (nonlinear.cc:356-357)
         active = false;
@@ -1004,7 +1271,21 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
     if (active) {
       // ---- QP step ------------------------------------------------------------------------------------------------
       double cdx = 0.0;
-      const bool qp_ok = riccati_qp<L, PL>(c, w, lambda, x_cur, set_point, cdx);
+      bool qp_ok;
+      if (k.condensed && !(lambda > 0.0)) {
+        qp_ok = condensed_qp<L, PL>(c, w, tri_valid, x_cur, set_point, cdx);
+        if (!qp_ok) {
+          // The NX x NX multiplier system of the condensed form lost positive definiteness (0.1 % of double-pendulum
+          // instances: open-loop sensitivity rows nearly dependent).  That is a property of the formulation, not of
+          // the QP: let the closed-loop Riccati recursion decide whether the reduced Hessian is indefinite.
+          tri_valid = false;
+          fill_gradient();
+          qp_ok = riccati_qp<L, PL>(c, w, lambda, x_cur, set_point, cdx);
+        }
+      } else {
+        tri_valid = false;  // the Riccati stage matrix shares the scratch of the tridiagonal factor
+        qp_ok = riccati_qp<L, PL>(c, w, lambda, x_cur, set_point, cdx);
+      }
       if (!qp_ok) {
         res.termination = TS_QP_INDEFINITE;
         active = false;
