@@ -665,8 +665,8 @@ def main():
     if rank == 0:
         s1, d1, p1 = states_h[:1].copy(), dyn_h[:1].copy(), sp_h[:1].copy()
 
-        def batch1_latency(low_latency):
-            one = BatchedOptimization(1, device=local_rank, low_latency=low_latency)
+        def batch1_latency(low_latency, min_latency=False):
+            one = BatchedOptimization(1, device=local_rank, low_latency=low_latency, min_latency=min_latency)
             ts = []
             for i in range(60):
                 one.reset()
@@ -678,9 +678,13 @@ def main():
 
         p50, p99 = batch1_latency(False)
         p50_ll, p99_ll = batch1_latency(True)
+        p50_ml, p99_ml = batch1_latency(False, True)
         lat = {"p50_ms": p50, "p99_ms": p99, "batch": 1, "path": "cpmpc_step (host buffers), default mapping",
                "low_latency_flag": {"p50_ms": p50_ll, "p99_ms": p99_ll,
-                                    "note": "CPMPC_FLAG_LOW_LATENCY: two lanes per shooting segment"}}
+                                    "note": "CPMPC_FLAG_LOW_LATENCY: two lanes per shooting segment"},
+               "min_latency_flag": {"p50_ms": p50_ml, "p99_ms": p99_ml,
+                                    "note": "CPMPC_FLAG_MIN_LATENCY: one warp per instance, 5 linearisation chunks "
+                                            "per segment"}}
 
     # ---- reduce over ranks: max time, summed work -----------------------------------------------------------------
     per_rank = None

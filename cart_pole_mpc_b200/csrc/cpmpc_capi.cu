@@ -275,6 +275,15 @@ int cpmpc_create_ex(const cpmpc_params* params, int64_t batch, int device, uint3
   if ((flags & CPMPC_FLAG_LOW_LATENCY) != 0u && 2 * base_lanes <= 32 && k.S >= 2 && (2 * base_lanes) / k.nseg >= 2) {
     lanes = 2 * base_lanes;
   }
+  // CPMPC_FLAG_MIN_LATENCY: a whole warp per instance.  The chunk count is the smallest one that reaches the shortest
+  // possible chunk (ceil(S / floor(32 / segments)) knots): 5 chunks of 2 knots at the defaults, not 8 ragged ones.
+  int min_latency_cps = 0;
+  if ((flags & CPMPC_FLAG_MIN_LATENCY) != 0u && k.S >= 2 && 32 / k.nseg >= 2) {
+    const int max_cps = (32 / k.nseg < k.S) ? 32 / k.nseg : k.S;
+    const int chain = (k.S + max_cps - 1) / max_cps;
+    min_latency_cps = (k.S + chain - 1) / chain;
+    lanes = 32;
+  }
   if (const char* env = std::getenv("CPMPC_LANES")) {
     const int v = std::atoi(env);
     if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) lanes = v;
@@ -296,6 +305,7 @@ int cpmpc_create_ex(const cpmpc_params* params, int64_t batch, int device, uint3
     k.cps = chunked ? (2 * base_lanes) / k.nseg : 1;
     if (k.cps < 1) k.cps = 1;
     if (k.cps > k.S) k.cps = k.S;
+    if (min_latency_cps > 0 && min_latency_cps * k.nseg <= lanes) k.cps = min_latency_cps;
     if (const char* env = std::getenv("CPMPC_CHUNKS")) {
       const int v = std::atoi(env);
       if (v >= 1 && v <= k.S && v * k.nseg <= lanes) k.cps = v;

@@ -160,10 +160,11 @@ inline cpmpc_params ToC(const OptimizationParams& p) {
 // entry points used by callers that keep their data on the GPU.
 class BatchedOptimization {
  public:
-  BatchedOptimization(const OptimizationParams& params, std::size_t batch, int device = 0)
+  // `flags`: 0 (throughput mapping), CPMPC_FLAG_LOW_LATENCY or CPMPC_FLAG_MIN_LATENCY (include/cpmpc.h)
+  BatchedOptimization(const OptimizationParams& params, std::size_t batch, int device = 0, std::uint32_t flags = 0)
       : params_(params), batch_(batch) {
     const cpmpc_params c = detail::ToC(params);
-    detail::Check(cpmpc_create(&c, static_cast<int64_t>(batch), device, &handle_));
+    detail::Check(cpmpc_create_ex(&c, static_cast<int64_t>(batch), device, flags, &handle_));
   }
   ~BatchedOptimization() { cpmpc_destroy(handle_); }
   BatchedOptimization(const BatchedOptimization&) = delete;

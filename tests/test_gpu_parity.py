@@ -447,6 +447,24 @@ def test_low_latency_mapping_matches_oracle(oracle):
         assert (out.stats["n_iterations"] == ora.n_iterations).mean() >= 0.98
 
 
+@pytest.mark.parametrize("over", [dict(), dict(state_spacing=5, max_iterations=10), dict(state_spacing=40),
+                                  dict(window_length=80, state_spacing=10), dict(window_length=20, state_spacing=2)])
+def test_min_latency_mapping_matches_oracle(oracle, over):
+    """CPMPC_FLAG_MIN_LATENCY (one warp per instance, up to 32 / segments linearisation chunks per segment, ragged
+    chunk lengths included) against the oracle, same parity bar as the default mapping; and a batch of one equals the
+    same instance inside a batch (the mapping, not the batch composition, decides the rounding)."""
+    from cart_pole_mpc_b200 import BatchedOptimization, synthetic
+    B = 256
+    st, dy, sp = synthetic.swingup_batch(B, seed=11)
+    ora = oracle.batch_step(oracle.opt_array(**over), st, dy, sp, want_iter_log=False)
+    out = BatchedOptimization(B, min_latency=True, **over).step(st, dy, sp)
+    rel = np.abs(out.merit - ora.merit) / np.maximum(np.abs(ora.merit), 1e-300)
+    assert (rel <= REL_COST_TOL).mean() >= (0.90 if over.get("state_spacing") == 40 else 0.95)
+    assert (out.stats["n_iterations"] == ora.n_iterations).mean() >= 0.98
+    one = BatchedOptimization(1, min_latency=True, **over).step(st[3:4], dy[3:4], sp[3:4])
+    assert np.array_equal(one.u[0], out.u[3]) and np.array_equal(one.stats[0], out.stats[3])
+
+
 def test_sharding_two_handles_equal_one(oracle):
     """Multi-GPU data path in miniature: two handles over the two halves == one handle over the whole batch."""
     from cart_pole_mpc_b200 import synthetic
