@@ -7,8 +7,10 @@
 // subclasses (the reference throws assert::default_error : std::exception, mini_opt/assertions.hpp:49-73); numerical
 // outcomes stay in-band in the per-instance statistics.
 #pragma once
+#include <charconv>
 #include <cstddef>
 #include <cstdint>
+#include <cstdio>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -42,6 +44,37 @@ enum class StepSizeSelectionResult : int {
 // mini_opt/structs.hpp:159-164
 enum class OptimizerState : int { NOMINAL = 0, ATTEMPTING_RESTORE_LM = 1 };
 
+// Names as printed by the reference's ostream operators (mini_opt/source/structs.cc:17-120).
+inline const char* ToName(NLSTerminationState s) {
+  static const char* const names[] = {"MAX_ITERATIONS",  "SATISFIED_ABSOLUTE_TOL", "SATISFIED_RELATIVE_TOL",
+                                      "SATISFIED_FIRST_ORDER_TOL", "MAX_LAMBDA", "QP_INDEFINITE", "USER_CALLBACK"};
+  const int i = static_cast<int>(s);
+  return (i >= 0 && i < 7) ? names[i] : "REJECTED_NON_FINITE";
+}
+inline const char* ToName(StepSizeSelectionResult r) {
+  static const char* const names[] = {"SUCCESS", "MAX_ITERATIONS", "FIRST_ORDER_SATISFIED", "POSITIVE_DERIVATIVE",
+                                      "FAILURE_NON_FINITE_COST", "FAILURE_INVALID_ALPHA"};
+  const int i = static_cast<int>(r);
+  return (i >= 0 && i < 6) ? names[i] : "?";
+}
+inline const char* ToName(OptimizerState s) {
+  return s == OptimizerState::NOMINAL ? "NOMINAL" : "ATTEMPTING_RESTORE_LM";
+}
+
+namespace detail {
+// fmt's "{}" for a double: the shortest decimal string that round-trips
+inline std::string Shortest(double v) {
+  char buf[40];
+  const auto r = std::to_chars(buf, buf + sizeof(buf), v);
+  return std::string(buf, r.ptr);
+}
+inline std::string Printf(const char* format, double v) {
+  char buf[64];
+  std::snprintf(buf, sizeof(buf), format, v);
+  return buf;
+}
+}  // namespace detail
+
 // mini_opt/structs.hpp:169-212
 struct Errors {
   double f{0};
@@ -67,6 +100,30 @@ struct NLSIteration {
   double penalty;
   StepSizeSelectionResult step_result;
   std::vector<LineSearchStep> line_search_steps;
+
+  // Same lines as NLSIteration::ToString (mini_opt/source/structs.cc:159-218) without colour codes; the QP line is
+  // always the null-space solver's SUCCESS (an indefinite QP ends the solve before the iteration is logged).
+  std::string ToString() const {
+    using detail::Printf;
+    using detail::Shortest;
+    std::string r = "Iteration # " + std::to_string(iteration) + ", state = " + ToName(optimizer_state) +
+                    ", lambda = " + Shortest(lambda) + "\n";
+    r += "  f(0): " + Printf("%.16e", errors_initial.f) + ", c(0): " + Printf("%.16e", errors_initial.equality) +
+         ", total: " + Printf("%.16e", errors_initial.Total(penalty)) + "\n";
+    r += "  penalty = " + Printf("%.16f", penalty) + "\n";
+    r += "  QP: SUCCESS\n";
+    r += "  df/dalpha = " + Shortest(directional_derivatives.d_f) + ", dc/dalpha = " +
+         Shortest(directional_derivatives.d_equality) + "\n";
+    r += std::string("  Search result: ") + ToName(step_result) + "\n";
+    std::size_t i = 0;
+    for (const LineSearchStep& step : line_search_steps) {
+      const std::string n = std::to_string(i++);
+      r += "  f(" + n + "): " + Printf("%.16e", step.errors.f) + ", c(" + n + "): " +
+           Printf("%.16e", step.errors.equality) + ", total: " + Printf("%.16e", step.errors.Total(penalty)) +
+           ", alpha = " + Printf("%.10f", step.alpha) + "\n";
+    }
+    return r;
+  }
 };
 
 // mini_opt/structs.hpp:329-347
@@ -87,6 +144,13 @@ struct NLSSolverOutputs {
             it.step_result != StepSizeSelectionResult::FIRST_ORDER_SATISFIED);
     }
     return n;
+  }
+  // mini_opt/source/structs.cc:256-266
+  std::string ToString() const {
+    std::string r;
+    for (const auto& it : iterations) r += it.ToString();
+    r += std::string("  termination = ") + ToName(termination_state) + "\n";
+    return r;
   }
 };
 

@@ -71,6 +71,12 @@ class OptimizationOutputs:
         self.stats = stats
         self._iter_log = iter_log
 
+    @staticmethod
+    def _g(x) -> str:
+        """fmt's "{}" for a double: shortest round-trip digits, no trailing ".0"."""
+        t = repr(float(x))
+        return t[:-2] if t.endswith(".0") else t
+
     def solver_summary(self) -> str:
         """Same line layout as mini_opt::NLSSolverOutputs::ToString (mini_opt/source/structs.cc:159-268)."""
         lines = []
@@ -79,11 +85,11 @@ class OptimizationOutputs:
             r = self._iter_log[i]
             state = "NOMINAL" if int(r[0]) == 0 else "ATTEMPTING_RESTORE_LM"
             pen = r[6]
-            lines.append(f"Iteration # {i}, state = {state}, lambda = {r[1]}")
+            lines.append(f"Iteration # {i}, state = {state}, lambda = {self._g(r[1])}")
             lines.append(f"  f(0): {r[2]:.16e}, c(0): {r[3]:.16e}, total: {r[2] + pen * r[3]:.16e}")
             lines.append(f"  penalty = {pen:.16f}")
             lines.append("  QP: SUCCESS")
-            lines.append(f"  df/dalpha = {r[4]}, dc/dalpha = {r[5]}")
+            lines.append(f"  df/dalpha = {self._g(r[4])}, dc/dalpha = {self._g(r[5])}")
             lines.append(f"  Search result: {_b.STEP_RESULT_NAMES.get(int(r[7]), '?')}")
             for s in range(min(int(r[8]), 6)):
                 a, f, c = r[9 + 3 * s], r[10 + 3 * s], r[11 + 3 * s]

@@ -3,6 +3,7 @@
 // Build: g++ -std=c++17 facade_closed_loop.cc -L<pkg> -lcpmpc ; exit code 0 == every assertion of the reference holds.
 #include <cmath>
 #include <cstdio>
+#include <string>
 #include <vector>
 
 #include "../../cart_pole_mpc_b200/host/optimization.hpp"
@@ -67,6 +68,23 @@ int main() {
     if (t == 1 && outputs.previous_solution.size() != 4 * 9 + 40) {
       std::printf("previous_solution has the wrong size\n");
       return 1;
+    }
+    if (t == 0) {
+      // NLSSolverOutputs::ToString (mini_opt/source/structs.cc:159-266): one block per iteration + the termination line
+      const std::string summary = outputs.solver_outputs.ToString();
+      std::size_t blocks = 0;
+      for (std::size_t pos = summary.find("Iteration # "); pos != std::string::npos;
+           pos = summary.find("Iteration # ", pos + 1)) {
+        ++blocks;
+      }
+      if (blocks != outputs.solver_outputs.iterations.size() ||
+          summary.find("Iteration # 0, state = NOMINAL, lambda = 0\n") != 0 ||
+          summary.find("  QP: SUCCESS\n") == std::string::npos ||
+          summary.find("  termination = ") == std::string::npos) {
+        std::printf("unexpected solver summary:\n%s", summary.c_str());
+        return 1;
+      }
+      std::printf("SUMMARY_BEGIN\n%sSUMMARY_END\n", summary.c_str());
     }
     total_iterations += outputs.solver_outputs.iterations.size();
     const SingleCartPoleState& terminal_state = outputs.predicted_states.back();

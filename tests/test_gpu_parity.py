@@ -495,3 +495,12 @@ def test_cpp_facade_runs_the_reference_closed_loop_test(tmp_path):
     proc = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout + proc.stderr
     assert "FACADE_CLOSED_LOOP_OK" in proc.stdout
+    # NLSSolverOutputs::ToString of the C++ facade == solver_summary() of the Python mirror for the same first solve
+    # (same kernel, batch of one): the two host layers format the reference's summary identically
+    cpp_summary = proc.stdout.split("SUMMARY_BEGIN\n")[1].split("SUMMARY_END")[0]
+    from cart_pole_mpc_b200 import pypendulum as pp
+    op = pp.OptimizationParams()
+    op.control_dt, op.window_length, op.state_spacing, op.max_iterations = 0.01, 40, 5, 10
+    dyn = pp.SingleCartPoleParams(1.0, 0.1, 0.25, 9.81, 0.03, 0.1, 0.13, 0.8, 100.0)
+    out = pp.Optimization(op).step(pp.SingleCartPoleState(0.0, -math.pi / 2, 0.0, 0.0), dyn, 0.0)
+    assert out.solver_summary() == cpp_summary
