@@ -149,8 +149,18 @@ def cpu_impl(prefer_ref=True):
     return contextlib.nullcontext, "port"
 
 
+def host_threads():
+    """All host threads this process may use.  Passed explicitly to the CPU legs: torchrun exports OMP_NUM_THREADS=1
+    to every rank, which would silently turn the reference arm into a single-threaded run at N > 1."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(states, dyn, sp, repeats=3, n_threads=0, prefer_ref=True):
     from oracle import oracle_py
+    n_threads = n_threads or host_threads()
     ctx, kind = cpu_impl(prefer_ref)
     opt = oracle_py.opt_array()
     best = None
@@ -181,10 +191,11 @@ def run_reference(args):
     res = None
     with ctx():
         for _ in range(args.warmup):
-            threads = oracle_py.batch_step(opt, states[:256], dyn[:256], sp[:256], want_iter_log=False).threads
+            threads = oracle_py.batch_step(opt, states[:256], dyn[:256], sp[:256], want_iter_log=False,
+                                           n_threads=host_threads()).threads
         for _ in range(args.steps):
             t0 = time.perf_counter()
-            res = oracle_py.batch_step(opt, states, dyn, sp, want_iter_log=False)
+            res = oracle_py.batch_step(opt, states, dyn, sp, want_iter_log=False, n_threads=host_threads())
             times.append(time.perf_counter() - t0)
             threads = res.threads
     total = float(np.sum(times))
@@ -325,7 +336,7 @@ def run_closed_loop(args):
         with ctx():
             t0 = time.perf_counter()
             _, ctl_o, _, cnt_o, _, thr = oracle_py.closed_loop(oracle_py.opt_array(**over), st_h[:nb], dy_h[:nb],
-                                                               sp_h[:nb], nt)
+                                                               sp_h[:nb], nt, n_threads=host_threads())
             dt_cpu = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": nb * nt / dt_cpu, "unit": UNIT, "cores": int(thr), "kind": kind,
                                 "sample": f"the first {nb} plants x {nt} control steps, one plant per thread"}
@@ -414,7 +425,7 @@ def run_sweep(args):
         with ctx():
             t0 = time.perf_counter()
             ora = oracle_py.batch_step(oracle_py.opt_array(window_length=W, state_spacing=S), st_h[:nb], dy_h[:nb],
-                                       sp_h[:nb], weights=wt_h[:nb], want_iter_log=False)
+                                       sp_h[:nb], weights=wt_h[:nb], want_iter_log=False, n_threads=host_threads())
             dt_cpu = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": nb / dt_cpu, "unit": UNIT, "cores": int(ora.threads), "kind": kind,
                                 "sample": f"the first {nb} instances, one instance per thread"}
@@ -505,7 +516,8 @@ def run_double(args):
         from oracle import oracle_py
         nb = min(B, 2048)
         t0 = time.perf_counter()
-        ora = oracle_py.dp_batch_step(oracle_py.dp_opt_array(), st_h[:nb], dy_h[:nb], sp_h[:nb], want_iter_log=False)
+        ora = oracle_py.dp_batch_step(oracle_py.dp_opt_array(), st_h[:nb], dy_h[:nb], sp_h[:nb], want_iter_log=False,
+                                      n_threads=host_threads())
         dt_cpu = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": nb / dt_cpu, "unit": UNIT, "cores": int(ora.threads), "kind": "port",
                                 "sample": f"the first {nb} instances, one instance per thread (nx=6 oracle; the "
