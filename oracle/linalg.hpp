@@ -73,6 +73,7 @@ struct ColPivQR {
   std::vector<int> perm;  // perm[j] = original column placed at position j
   int nonzero_pivots{0};
   double max_pivot{0.0};
+  Vec wbuf;  // scratch of the reflector application
 
   void Compute(const Mat& m) {
     qr = m;
@@ -131,13 +132,30 @@ struct ColPivQR {
       qr(k, k) = beta;
       if (std::abs(beta) > max_pivot) max_pivot = std::abs(beta);
 
-      // apply H_k = I - tau v v^T (v = [1; essential]) to the trailing columns
-      for (int j = k + 1; j < cols; ++j) {
-        double w = qr(k, j);
-        for (int i = k + 1; i < rows; ++i) w += qr(i, k) * qr(i, j);
-        w *= tau[k];
-        qr(k, j) -= w;
-        for (int i = k + 1; i < rows; ++i) qr(i, j) -= qr(i, k) * w;
+      // apply H_k = I - tau v v^T (v = [1; essential]) to the trailing columns.  Swept row by row (the storage is
+      // row-major) so that the compiler can vectorise across the columns j; every w[j] and every qr(i, j) still sees
+      // exactly the same operations in the same order as the column-by-column form.
+      if (k + 1 < cols) {
+        wbuf.assign(static_cast<std::size_t>(cols), 0.0);
+        double* w = wbuf.data();
+        const double* rk = &qr(k, 0);
+        for (int j = k + 1; j < cols; ++j) w[j] = rk[j];
+        for (int i = k + 1; i < rows; ++i) {
+          const double vi = qr(i, k);
+          const double* ri = &qr(i, 0);
+          for (int j = k + 1; j < cols; ++j) w[j] += vi * ri[j];
+        }
+        const double tk = tau[k];
+        double* rkw = &qr(k, 0);
+        for (int j = k + 1; j < cols; ++j) {
+          w[j] *= tk;
+          rkw[j] -= w[j];
+        }
+        for (int i = k + 1; i < rows; ++i) {
+          const double vi = qr(i, k);
+          double* ri = &qr(i, 0);
+          for (int j = k + 1; j < cols; ++j) ri[j] -= vi * w[j];
+        }
       }
 
       // down-date the tracked column norms
@@ -175,13 +193,27 @@ struct ColPivQR {
     const int size = std::min(qr.rows, qr.cols);
     Mat Q(rows, rows);
     for (int i = 0; i < rows; ++i) Q(i, i) = 1.0;
+    Vec wv(static_cast<std::size_t>(rows), 0.0);
+    double* w = wv.data();
     for (int k = size - 1; k >= 0; --k) {
+      // same row-by-row sweep as in Compute(): identical arithmetic per entry, contiguous inner loops
+      const double* qk = &Q(k, 0);
+      for (int j = k; j < rows; ++j) w[j] = qk[j];
+      for (int i = k + 1; i < rows; ++i) {
+        const double vi = qr(i, k);
+        const double* qi = &Q(i, 0);
+        for (int j = k; j < rows; ++j) w[j] += vi * qi[j];
+      }
+      const double tk = tau[k];
+      double* qkw = &Q(k, 0);
       for (int j = k; j < rows; ++j) {
-        double w = Q(k, j);
-        for (int i = k + 1; i < rows; ++i) w += qr(i, k) * Q(i, j);
-        w *= tau[k];
-        Q(k, j) -= w;
-        for (int i = k + 1; i < rows; ++i) Q(i, j) -= qr(i, k) * w;
+        w[j] *= tk;
+        qkw[j] -= w[j];
+      }
+      for (int i = k + 1; i < rows; ++i) {
+        const double vi = qr(i, k);
+        double* qi = &Q(i, 0);
+        for (int j = k; j < rows; ++j) qi[j] -= vi * w[j];
       }
     }
     return Q;
