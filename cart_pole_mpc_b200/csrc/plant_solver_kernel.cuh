@@ -1271,18 +1271,16 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
     if (active) {
       // ---- QP step ------------------------------------------------------------------------------------------------
       double cdx = 0.0;
-      bool qp_ok;
-      if (k.condensed && !(lambda > 0.0)) {
+      const bool try_condensed = k.condensed && !(lambda > 0.0);
+      bool qp_ok = false;
+      if (try_condensed) {
         qp_ok = condensed_qp<L, PL>(c, w, tri_valid, x_cur, set_point, cdx);
-        if (!qp_ok) {
-          // The NX x NX multiplier system of the condensed form lost positive definiteness (0.1 % of double-pendulum
-          // instances: open-loop sensitivity rows nearly dependent).  That is a property of the formulation, not of
-          // the QP: let the closed-loop Riccati recursion decide whether the reduced Hessian is indefinite.
-          tri_valid = false;
-          fill_gradient();
-          qp_ok = riccati_qp<L, PL>(c, w, lambda, x_cur, set_point, cdx);
-        }
-      } else {
+        // The NX x NX multiplier system of the condensed form lost positive definiteness (0.1 % of double-pendulum
+        // instances: open-loop sensitivity rows nearly dependent).  That is a property of the formulation, not of
+        // the QP: restore the gradient and let the closed-loop Riccati recursion decide.
+        if (!qp_ok) fill_gradient();
+      }
+      if (!qp_ok) {
         tri_valid = false;  // the Riccati stage matrix shares the scratch of the tridiagonal factor
         qp_ok = riccati_qp<L, PL>(c, w, lambda, x_cur, set_point, cdx);
       }

@@ -1000,6 +1000,23 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
   res.n_failed = 0;
   res.last_step_result = SR_SUCCESS;
 
+  // gradient of the control costs at the current controls into du[] (the QP routines consume and overwrite it)
+  auto fill_gradient = [&]() {
+    for (int col = c.gl; col < W; col += L) {
+      double g = 0.0;
+      const double uk = u[col];
+      if (w.w_r > 0.0) {
+        const double wr2 = w.w_r * w.w_r;
+        if (col + 1 < W) g += wr2 * (uk - u[col + 1]);
+        if (col > 0) g -= wr2 * (u[col - 1] - uk);
+        if (col == 0) g += wr2 * (uk - u_prev);
+      }
+      if (w.w_u > 0.0) g += (w.w_u * w.w_u) * uk;
+      du[col] = g;
+    }
+    CPMPC_GSYNC();
+  };
+
   for (int iter = 0; iter < k.max_iter; ++iter) {
     if (!__any_sync(0xffffffffu, active)) break;
 
@@ -1147,19 +1164,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
       }
 
       // gradient of the control costs, c_u = J^T r (optimization.cc:270-301), parked in du[]
-      for (int col = c.gl; col < W; col += L) {
-        double g = 0.0;
-        const double uk = u[col];
-        if (w.w_r > 0.0) {
-          const double wr2 = w.w_r * w.w_r;
-          if (col + 1 < W) g += wr2 * (uk - u[col + 1]);
-          if (col > 0) g -= wr2 * (u[col - 1] - uk);
-          if (col == 0) g += wr2 * (uk - u_prev);
-        }
-        if (w.w_u > 0.0) g += (w.w_u * w.w_u) * uk;
-        du[col] = g;
-      }
-      CPMPC_GSYNC();
+      fill_gradient();
 
       if (!isfinite(f0) || !isfinite(eq0)) {
         // The reference throws here (nonlinear.cc:356-357); the batch reports it per instance instead.
@@ -1172,9 +1177,15 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
       // ---- QP step (qp.cc:679-729) -----------------------------------------------------------------------------
       double cdx = 0.0;
       bool qp_ok;
-      if (k.condensed && !(lambda > 0.0)) {
+      const bool try_condensed = k.condensed && !(lambda > 0.0);
+      qp_ok = false;
+      if (try_condensed) {
         qp_ok = condensed_qp<L>(c, w, tri_valid, x_cur, target, cdx);
-      } else {
+        // A failed 4x4 multiplier system is a property of the condensed formulation (open-loop sensitivity rows nearly
+        // dependent), not necessarily of the QP: restore the gradient and let the Riccati recursion decide.
+        if (!qp_ok) fill_gradient();
+      }
+      if (!qp_ok) {
         tri_valid = false;  // the Riccati stage matrix shares the scratch of the tridiagonal factor
         qp_ok = riccati_qp<L>(c, w, lambda, x_cur, target, cdx);
       }
