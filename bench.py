@@ -85,13 +85,14 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.stamps = []
         self.thread = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
             return
@@ -99,11 +100,15 @@ class ClockSampler:
         def pump():
             for line in self.proc.stdout:
                 self.lines.append(line.strip())
+                self.stamps.append(time.perf_counter())
 
         self.thread = threading.Thread(target=pump, daemon=True)
         self.thread.start()
 
-    def stop(self):
+    def stop(self, window=None):
+        """`window` = (t0, t1) in perf_counter time: only samples taken inside it count.  When the timed region is
+        shorter than the sampling period and holds no sample, the samples of the warm-up steps (same kernel, same
+        load, started before the timed region) are used instead and `scope` says so."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         self.proc.terminate()
@@ -111,9 +116,16 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+        lines, scope = list(self.lines), "whole run"
+        if window is not None:
+            inside = [ln for ln, t in zip(self.lines, self.stamps) if window[0] <= t <= window[1]]
+            if inside:
+                lines, scope = inside, "timed region"
+            else:
+                lines, scope = list(self.lines), "same kernel under load around the timed region (region shorter than one sample)"
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in lines:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -125,8 +137,11 @@ class ClockSampler:
             for name, val in zip(names, parts[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(smax)) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(smax)) if smax else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if window is not None:
+            out["scope"] = scope
+        return out
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -604,6 +619,10 @@ def main():
             dist.all_gather_into_tensor(gathered_u, u_d)
             dist.all_gather_into_tensor(gathered_stats, stats_d)
 
+    # every rank samples its own GPU (a slow or throttled GPU decides the max-over-ranks time); started before the
+    # warm-up because nvidia-smi needs ~0.1 s to produce its first line and the timed region can be that short
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         flush.fill_(1)
         one_step()
@@ -611,17 +630,12 @@ def main():
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
-
-    sampler = ClockSampler(local_rank)
-    # every rank samples its own GPU: a slow or throttled GPU decides the max-over-ranks time
-    sampler.start()
     launches0 = launch_count()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     t_wall0 = time.perf_counter()
     # Give the host a few ms of head start (untimed device work) so that a descheduled Python thread cannot leave the
-    # GPU idle between a step's start event and its kernel: with 8 ranks on a 16-core host that inflated one rank's
-    # per-step time by 40 % although every kernel took the same 0.81 ms.
+    # GPU idle between a step's start event and its kernel (8 ranks share a 16-core host).
     for _ in range(32):
         flush.fill_(0)
     for i in range(args.steps):
@@ -637,7 +651,15 @@ def main():
     launches = launch_count() - launches0
     step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, stops)])
     total_ms = float(step_ms.sum())
-    clocks = sampler.stop()
+    if not sampler.lines and sampler.proc is not None:
+        # the whole run was shorter than nvidia-smi's start-up: keep the same kernel running (untimed) until one
+        # sample exists, so that the clocks line always describes the GPU under this load
+        t_extra = time.perf_counter()
+        while not sampler.lines and time.perf_counter() - t_extra < 3.0:
+            solver.reset_device()  # the kernel only: ranks leave this loop at different times, so no collective here
+            solver.step_device(states_d, dyn_d, sp_d, u_d, pred_out=pred_d, stats_out=stats_d)
+            torch.cuda.synchronize()
+    clocks = sampler.stop(window=(t_wall0, t_wall0 + t_wall))
 
     stats = np.frombuffer(stats_d.cpu().numpy().tobytes(), dtype=_capi.STATS_DTYPE)
     n_iter_sum = float(stats["n_iterations"].sum())
