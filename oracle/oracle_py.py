@@ -41,7 +41,8 @@ def opt_array(**overrides) -> np.ndarray:
 
 def build(force: bool = False) -> str:
     """Compile liboracle.so and oracle_kat with the committed Makefile (g++ only, seconds)."""
-    if force or not os.path.exists(_LIB_PATH) or not os.path.exists(os.path.join(_HERE, "oracle_kat")):
+    if (force or not os.path.exists(_LIB_PATH) or not os.path.exists(os.path.join(_HERE, "oracle_kat"))
+            or not os.path.exists(os.path.join(_HERE, "shim_selftest"))):
         subprocess.run(["make", "-C", _HERE, "-j4"], check=True, capture_output=True)
     return _LIB_PATH
 

@@ -250,3 +250,15 @@ def test_invalid_params_throw_in_the_compiled_reference_too(oracle):
         with oracle.using_ref():
             with pytest.raises(ValueError):
                 oracle.Optimization(oracle.opt_array(**bad))
+
+
+def test_eigen_shim_selftest(oracle):
+    """oracle/shim_selftest.cc: every Eigen operation the reference's sources spell (views that write through,
+    fixed/dynamic construction, products in accumulation order, self-adjoint / triangular views, LLT, column-pivoted
+    QR with its permutation, the particular-solution formula of qp.cc:703-706, LDLT / eigenvalues / IOFormat stubs)
+    checked against plain loops.  Needs neither the reference nor a GPU."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    proc = subprocess.run([os.path.join(ROOT, "oracle", "shim_selftest")], capture_output=True, text=True, timeout=60)
+    assert proc.returncode == 0 and "SHIM_SELFTEST_OK" in proc.stdout, proc.stdout + proc.stderr
