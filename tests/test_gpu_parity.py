@@ -266,6 +266,29 @@ def test_variants_against_compiled_reference_live(oracle, over, min_frac):
     assert np.median(dpred) < 1e-9
 
 
+@pytest.mark.parametrize("over,min_frac", [
+    (dict(window_length=400, state_spacing=10), 0.6),                      # 40 segments > 32 lanes, 4 s horizon
+    (dict(window_length=330, state_spacing=10, max_iterations=4), 0.9),    # 33 segments: ragged over the lanes
+    (dict(window_length=64, state_spacing=1, max_iterations=3), 0.9),      # one knot per segment, 64 segments
+    (dict(window_length=100, state_spacing=100, max_iterations=3), 0.9),   # single shooting with a 100-knot segment
+])
+def test_maximum_sizes_against_compiled_reference_live(oracle, over, min_frac):
+    """Problem shapes at the edges of the lane mapping (more segments than lanes, one-knot segments, one huge
+    segment): must agree with the reference's own code, not just run."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/libref.so not present")
+    from cart_pole_mpc_b200 import synthetic
+    B = 16
+    st, dy, sp = synthetic.swingup_batch(B, seed=5)
+    with oracle.using_ref():
+        ref = oracle.batch_step(oracle.opt_array(**over), st, dy, sp, want_iter_log=False)
+    out = _solver(B, **over).step(st, dy, sp)
+    rel = _rel_cost(out, ref.stats)
+    assert (rel <= REL_COST_TOL).mean() >= min_frac
+    assert (out.stats["n_iterations"] == ref.n_iterations).mean() >= 0.9
+    assert (out.stats["termination_state"] == ref.termination).mean() >= 0.9
+
+
 def test_warm_started_step_against_compiled_reference_live(oracle):
     """Step 2 of a receding horizon: both sides are handed the same previous solution (SetPreviousSolution,
     optimization.hpp:86-89) and the same advanced plant state; covers the shift of the controls and u_prev
