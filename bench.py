@@ -801,6 +801,40 @@ def main():
 
     if per_rank is not None:
         line["per_rank"] = per_rank
+    if world == 1 and B == DEFAULT_BATCH and not args.no_cpu_baseline:
+        # Context for the roofline fraction (not the headline): the same kernel on a batch of several waves.  4096
+        # instances are ONE wave of warps, so the headline step time is the latency of the hardest instance; this
+        # line shows what the kernel sustains once every scheduler has work.
+        try:
+            Bl = 65536
+            st_l, dy_l, sp_l = synthetic.swingup_batch(Bl)
+            big = BatchedOptimization(Bl, device=local_rank)
+            to = lambda a: torch.from_numpy(a).to(dev)
+            st_ld, dy_ld, sp_ld = to(st_l), to(dy_l), to(sp_l)
+            u_l = torch.empty((Bl, W), dtype=torch.float64, device=dev)
+            pr_l = torch.empty((Bl, W, 4), dtype=torch.float64, device=dev)
+            stt_l = torch.empty((Bl, 56), dtype=torch.uint8, device=dev)
+            ms_l = []
+            for i in range(4):
+                big.reset_device()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                big.step_device(st_ld, dy_ld, sp_ld, u_l, pred_out=pr_l, stats_out=stt_l)
+                e1.record()
+                torch.cuda.synchronize()
+                if i > 0:
+                    ms_l.append(e0.elapsed_time(e1))
+            stl = np.frombuffer(stt_l.cpu().numpy().tobytes(), dtype=_capi.STATS_DTYPE)
+            fl = float(algorithmic_flops(stl["n_iterations"].astype(np.float64),
+                                         stl["n_line_search_steps"].astype(np.float64)).sum())
+            ms_med = float(np.median(ms_l))
+            line["large_batch"] = {"batch": Bl, "ms_per_step": ms_med, "value": Bl / (ms_med * 1e-3), "unit": UNIT,
+                                   "roofline_frac": fl / (ms_med * 1e-3) / 1e12 / peak_tflops if peak_tflops else None,
+                                   "note": "same kernel, 65536 cold-start instances (working set exceeds L2); "
+                                           "supplementary, not the headline configuration"}
+            big.close()
+        except Exception as exc:  # supplementary only: never fail the bench line over it
+            line["large_batch"] = {"error": str(exc)[:200]}
     if not args.no_cpu_baseline and world == 1:
         res, best, kind = cpu_baseline(states_h, dyn_h, sp_h, repeats=3)
         line["cpu_baseline"] = {"value": B / best, "unit": UNIT, "cores": res.threads, "kind": kind,
