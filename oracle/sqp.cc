@@ -109,21 +109,25 @@ QPNullSpaceTerminationState QPNullSpaceSolver::Solve(const QP& p) {
   }
 
   // G_reduced = Q2^T sym(G) Q2
+  // Both products are swept so that the innermost loop runs along a row of the row-major operands (the compiler
+  // vectorises it); every entry still receives its terms in increasing j (resp. i) starting from 0.0, i.e. exactly
+  // the sums of the plain dot-product form.
   Mat GQ2(N, Z);
   for (int i = 0; i < N; ++i) {
-    for (int z = 0; z < Z; ++z) {
-      double s = 0.0;
-      for (int j = 0; j <= i; ++j) s += p.G(i, j) * Q(j, rank + z);
-      for (int j = i + 1; j < N; ++j) s += p.G(j, i) * Q(j, rank + z);
-      GQ2(i, z) = s;
+    double* out = &GQ2(i, 0);
+    for (int j = 0; j < N; ++j) {
+      const double g = (j <= i) ? p.G(i, j) : p.G(j, i);
+      const double* qj = Q.a.data() + static_cast<std::size_t>(j) * Q.cols + rank;
+      for (int z = 0; z < Z; ++z) out[z] += g * qj[z];
     }
   }
   Mat Gr(Z, Z);
   for (int a = 0; a < Z; ++a) {
-    for (int b = 0; b < Z; ++b) {
-      double s = 0.0;
-      for (int i = 0; i < N; ++i) s += Q(i, rank + a) * GQ2(i, b);
-      Gr(a, b) = s;
+    double* out = &Gr(a, 0);
+    for (int i = 0; i < N; ++i) {
+      const double q = Q(i, rank + a);
+      const double* gi = &GQ2(i, 0);
+      for (int b = 0; b < Z; ++b) out[b] += q * gi[b];
     }
   }
 
