@@ -67,6 +67,8 @@ def main():
     if len(lmap) != len(rows):
         print(f"warning: {len(rows)} profiled vs {len(lmap)} disassembled instructions (library rebuilt?)")
     S, E, F = collections.Counter(), collections.Counter(), collections.Counter()
+    reasons = [h for h in ix if h.startswith("stall_") and "Not Issued" not in h]
+    R = collections.defaultdict(collections.Counter)  # phase -> stall reason -> samples
     ts = te = 0
     cur = "prologue"
     for i in range(n):
@@ -77,6 +79,10 @@ def main():
         e = int(rows[i][ix["Instructions Executed"]] or 0)
         S[cur] += s
         E[cur] += e
+        for h in reasons:
+            v = rows[i][ix[h]]
+            if v:
+                R[cur][h] += int(v)
         ts += s
         te += e
         txt = lmap[i][1]
@@ -90,6 +96,13 @@ def main():
             continue
         print(f"{k:14s} {100 * v / ts:6.1f} {100 * E[k] / te:7.1f} {100 * F[k] / max(1, E[k]):10.1f} "
               f"{(v / ts) / (E[k] / te + 1e-12):15.2f}")
+    if "--stalls" in sys.argv:
+        print("\nstall samples per phase (% of the phase's samples), top reasons")
+        for k, v in S.most_common():
+            if v < 0.01 * ts:
+                continue
+            top = ", ".join(f"{h[6:]} {100 * c / max(1, sum(R[k].values())):.0f}" for h, c in R[k].most_common(5))
+            print(f"{k:14s} {top}")
 
 
 if __name__ == "__main__":
