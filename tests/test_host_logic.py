@@ -231,3 +231,19 @@ def test_json_log_format_matches_the_reference_schema_and_round_trips():
     assert back.solver_summary() == out.solver_summary()
     assert np.array_equal(np.array(back.u), g["u"][0])
     assert "termination = MAX_ITERATIONS" in back.solver_summary()
+
+
+def test_header_is_plain_c99_and_links_from_c(cuda_lib, tmp_path):
+    """include/cpmpc.h is the drop-in boundary: it must be consumable from plain C (what cgo / JNI / ctypes generators
+    see), and a C program linked against libcpmpc.so must resolve its entry points.  Without a device the library
+    fails loudly (status code + message), it never falls back to a CPU path."""
+    from cart_pole_mpc_b200 import _capi
+    src = os.path.join(ROOT, "tests", "native", "abi_c_check.c")
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I" + inc, src], check=True)
+    pkg = os.path.dirname(_capi.LIB_PATH)
+    exe = tmp_path / "abi_c_check"
+    subprocess.run(["gcc", "-std=c99", "-I" + inc, src, "-L" + pkg, "-lcpmpc", "-Wl,-rpath," + pkg, "-o", str(exe)],
+                   check=True)
+    proc = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert proc.returncode == 0 and "ABI_C_OK version" in proc.stdout, proc.stdout + proc.stderr
