@@ -78,6 +78,9 @@ struct cpmpc_solver {
   long long* d_stats_sum = nullptr;
   double* d_controls = nullptr;
   long long controls_capacity = 0;
+  // small batches: one packed pinned host buffer and its device twin, so that a Step() costs one copy each way
+  unsigned char* h_pack = nullptr;
+  unsigned char* d_pack = nullptr;
 };
 
 namespace {
@@ -161,6 +164,53 @@ int EnsureStaging(cpmpc_solver* h) {
   CUDA_TRY(cudaMalloc(&h->d_pred, sizeof(double) * B * W * 4));
   CUDA_TRY(cudaMalloc(&h->d_stats, sizeof(cpmpc_stats) * B));
   CUDA_TRY(cudaMalloc(&h->d_stats_sum, sizeof(long long) * 4));
+  return CPMPC_OK;
+}
+
+// Step() for small batches (single solves above all): the six small transfers of the general path cost more host time
+// than the bytes they move, and pageable caller buffers make each of them a synchronous staged copy.  Inputs are
+// packed into one pinned buffer, cross the bus as ONE copy, the kernel reads and writes the device twin, and the
+// results come back as ONE copy.  Layout: [states B*4 | dyn B*9 | set_points B | weights B*6] then
+// [u B*W | predicted B*W*4 | stats B].
+constexpr long long kPackedBatchMax = 64;
+
+int StepPacked(cpmpc_solver* h, const double* states, const double* dyn_params, const double* set_points,
+               const double* weights, double* u_out, double* pred_out, cpmpc_stats* stats_out) {
+  const long long B = h->B;
+  const int W = h->cfg.W;
+  const size_t n_state = sizeof(double) * B * 4, n_dyn = sizeof(double) * B * CPMPC_DYN_STRIDE;
+  const size_t n_sp = sizeof(double) * B, n_w = sizeof(double) * B * CPMPC_WEIGHTS_STRIDE;
+  const size_t in_bytes = n_state + n_dyn + n_sp + n_w;
+  const size_t n_u = sizeof(double) * B * W, n_pred = sizeof(double) * B * W * 4, n_stats = sizeof(cpmpc_stats) * B;
+  const size_t out_bytes = n_u + n_pred + n_stats;
+  if (h->h_pack == nullptr) {
+    CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&h->h_pack), in_bytes + out_bytes));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->d_pack), in_bytes + out_bytes));
+  }
+  unsigned char* hp = h->h_pack;
+  std::memcpy(hp, states, n_state);
+  std::memcpy(hp + n_state, dyn_params, n_dyn);
+  std::memcpy(hp + n_state + n_dyn, set_points, n_sp);
+  if (weights != nullptr) std::memcpy(hp + n_state + n_dyn + n_sp, weights, n_w);
+  cudaStream_t s = h->stream;
+  unsigned char* dp = h->d_pack;
+  CUDA_TRY(cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, s));
+  unsigned char* dout = dp + in_bytes;
+  if (int rc = cpmpc_step_device(h, reinterpret_cast<double*>(dp), reinterpret_cast<double*>(dp + n_state),
+                                 reinterpret_cast<double*>(dp + n_state + n_dyn),
+                                 weights ? reinterpret_cast<double*>(dp + n_state + n_dyn + n_sp) : nullptr,
+                                 reinterpret_cast<double*>(dout),
+                                 pred_out ? reinterpret_cast<double*>(dout + n_u) : nullptr,
+                                 stats_out ? reinterpret_cast<cpmpc_stats*>(dout + n_u + n_pred) : nullptr, s)) {
+    return rc;
+  }
+  // only what the caller asked for comes back: [u] or [u | predicted] or everything
+  const size_t back = stats_out ? out_bytes : (pred_out ? n_u + n_pred : n_u);
+  CUDA_TRY(cudaMemcpyAsync(hp + in_bytes, dout, back, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  std::memcpy(u_out, hp + in_bytes, n_u);
+  if (pred_out != nullptr) std::memcpy(pred_out, hp + in_bytes + n_u, n_pred);
+  if (stats_out != nullptr) std::memcpy(stats_out, hp + in_bytes + n_u + n_pred, n_stats);
   return CPMPC_OK;
 }
 
@@ -391,6 +441,8 @@ int cpmpc_destroy(cpmpc_handle h) {
   cudaFree(h->d_stats);
   cudaFree(h->d_stats_sum);
   cudaFree(h->d_controls);
+  cudaFree(h->d_pack);
+  if (h->h_pack) cudaFreeHost(h->h_pack);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return CPMPC_OK;
@@ -428,6 +480,7 @@ int cpmpc_step(cpmpc_handle h, const double* states, const double* dyn_params, c
     return Fail(CPMPC_ERR_INVALID_ARGUMENT, "states, dyn_params, set_points and u_out are required");
   }
   CUDA_TRY(cudaSetDevice(h->device));
+  if (h->B <= kPackedBatchMax) return StepPacked(h, states, dyn_params, set_points, weights, u_out, pred_out, stats_out);
   if (int rc = EnsureStaging(h)) return rc;
   const long long B = h->B;
   const int W = h->cfg.W;

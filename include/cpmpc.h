@@ -103,8 +103,8 @@ int cpmpc_create(const cpmpc_params* params, int64_t batch, int device, cpmpc_ha
 #define CPMPC_FLAG_LOW_LATENCY 1u
 /*   CPMPC_FLAG_MIN_LATENCY  one full warp per instance: every shooting segment is linearised as up to 32 / segments
  *                           chunks side by side and the QP loops run 32 lanes wide.  The mapping for single solves
- *                           and batches below a few hundred instances (batch of one at the defaults: 0.46 ms against
- *                           0.53 ms with LOW_LATENCY and 0.64 ms with the default mapping); large batches lose most
+ *                           and batches below a few hundred instances (batch of one at the defaults: 0.43 ms against
+ *                           0.50 ms with LOW_LATENCY and 0.61 ms with the default mapping); large batches lose most
  *                           of their throughput.  Same rounding caveat as LOW_LATENCY.  Takes precedence over it. */
 #define CPMPC_FLAG_MIN_LATENCY 2u
 int cpmpc_create_ex(const cpmpc_params* params, int64_t batch, int device, uint32_t flags, cpmpc_handle* out);
