@@ -777,7 +777,23 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, boo
   for (int r = c.gl; r < 5; r += L) {
     double* row = (r < 4) ? (Z + r * W) : du;
     double prev = row[0];
-    for (int j = 1; j < W; ++j) {
+    // four elements per trip with the loads issued ahead of the dependent FMAs and the stores behind them: the
+    // compiler cannot move a load of row[j + 1] above the store of row[j] on its own (same array), and without that
+    // every element pays a shared-memory round trip on top of the FMA.  Same operations in the same order.
+    int j = 1;
+    for (; j + 4 <= W; j += 4) {
+      const double t0 = tl[j], t1 = tl[j + 1], t2 = tl[j + 2], t3 = tl[j + 3];
+      const double r0 = row[j], r1 = row[j + 1], r2 = row[j + 2], r3 = row[j + 3];
+      const double p0 = fma(-t0, prev, r0);
+      const double p1 = fma(-t1, p0, r1);
+      const double p2 = fma(-t2, p1, r2);
+      prev = fma(-t3, p2, r3);
+      row[j] = p0;
+      row[j + 1] = p1;
+      row[j + 2] = p2;
+      row[j + 3] = prev;
+    }
+    for (; j < W; ++j) {
       prev = fma(-tl[j], prev, row[j]);
       row[j] = prev;
     }
@@ -896,7 +912,20 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, boo
   if (c.gl == 0) {
     double nxt = du[W - 1];
     du[W - 1] = -nxt;
-    for (int j = W - 2; j >= 0; --j) {
+    int j = W - 2;
+    for (; j >= 3; j -= 4) {  // same batching as the forward substitution, descending
+      const double t0 = tl[j + 1], t1 = tl[j], t2 = tl[j - 1], t3 = tl[j - 2];
+      const double d0 = du[j], d1 = du[j - 1], d2 = du[j - 2], d3 = du[j - 3];
+      const double n0 = fma(-t0, nxt, d0);
+      const double n1 = fma(-t1, n0, d1);
+      const double n2 = fma(-t2, n1, d2);
+      nxt = fma(-t3, n2, d3);
+      du[j] = -n0;
+      du[j - 1] = -n1;
+      du[j - 2] = -n2;
+      du[j - 3] = -nxt;
+    }
+    for (; j >= 0; --j) {
       nxt = fma(-tl[j + 1], nxt, du[j]);
       du[j] = -nxt;
     }

@@ -83,7 +83,7 @@ def diff(a_path, b_path):
     for k in ta:
         print(f"{k:20s} {ta[k]:9.3f} ms -> {tb[k]:9.3f} ms   x{ta[k] / tb[k]:.3f}")
     bad = 0
-    for k in a.files:
+    for k in sorted(a.files):
         if k == "times":
             continue
         x, y = a[k], b[k]
