@@ -247,3 +247,45 @@ def test_header_is_plain_c99_and_links_from_c(cuda_lib, tmp_path):
                    check=True)
     proc = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     assert proc.returncode == 0 and "ABI_C_OK version" in proc.stdout, proc.stdout + proc.stderr
+
+
+def test_bench_clock_sampler_window_and_thread_count():
+    """bench.py helpers that decide what the JSON line says: samples inside the timed window win, an empty window
+    falls back to the samples around it (and says so), throttle reasons are collected, and the CPU legs ask for every
+    host thread explicitly (torchrun exports OMP_NUM_THREADS=1)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class FakeProc:
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            return 0
+
+    s = bench.ClockSampler(0)
+    s.proc = FakeProc()
+    s.lines = ["1200, 1965, 300.0, Not Active, Not Active, Not Active, Not Active",
+               "1965, 1965, 700.0, Not Active, Not Active, Not Active, Active",
+               "1950, 1965, 710.0, Not Active, Not Active, Not Active, Not Active"]
+    s.stamps = [1.0, 2.0, 2.5]
+    inside = s.stop(window=(1.5, 3.0))
+    assert inside["sm_mhz"] == 1957.5 and inside["samples"] == 2 and inside["scope"] == "timed region"
+    assert inside["reasons"] == ["sw_power_cap"] and inside["sm_max_mhz"] == 1965.0
+    s.proc = FakeProc()
+    empty = s.stop(window=(5.0, 6.0))
+    assert empty["samples"] == 3 and "shorter than one sample" in empty["scope"]
+    old = os.environ.get("OMP_NUM_THREADS")
+    os.environ["OMP_NUM_THREADS"] = "1"
+    try:
+        assert bench.host_threads() == len(os.sched_getaffinity(0)) >= 1
+    finally:
+        if old is None:
+            del os.environ["OMP_NUM_THREADS"]
+        else:
+            os.environ["OMP_NUM_THREADS"] = old
+    # the flop model the roofline uses reproduces the survey's two reference points (SURVEY.md 8d)
+    assert abs(bench.algorithmic_flops(8, 19) - 1.27e6) < 0.02e6
+    assert abs(bench.algorithmic_flops(3.3, 3.4) - 0.47e6) < 0.02e6
