@@ -289,3 +289,20 @@ def test_bench_clock_sampler_window_and_thread_count():
     # the flop model the roofline uses reproduces the survey's two reference points
     assert abs(bench.algorithmic_flops(8, 19) - 1.27e6) < 0.02e6
     assert abs(bench.algorithmic_flops(3.3, 3.4) - 0.47e6) < 0.02e6
+
+
+def test_reference_arm_under_torchrun_runs_on_rank_zero_with_all_threads(oracle):
+    """The driver launches `bench.py --impl reference` like the GPU arm (torchrun for N > 1): rank 0 alone prints the
+    line, the other ranks exit 0 without work, and the CPU run is not throttled to one thread by torchrun's
+    OMP_NUM_THREADS=1."""
+    import json
+    proc = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+         "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+         "--steps", "1", "--warmup", "1", "--batch", "128"], capture_output=True, text=True, timeout=300)
+    assert proc.returncode == 0, proc.stdout[-1500:] + proc.stderr[-1500:]
+    lines = [ln for ln in proc.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, lines
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
