@@ -84,5 +84,37 @@ def main():
     print("closed loop 8x60 counts", counts.tolist(), "hist", hist.tolist())
 
 
+def check_debug():
+    """Rebuilds the compiled reference with assertions on and -O1 (make -C oracle ref_debug) and requires it to
+    reproduce every committed ref_*.npz bit for bit: no shape assertion of the Eigen-interface shim may fire on the
+    path, and the fixtures must not depend on the optimisation level."""
+    import subprocess
+    subprocess.run(["make", "-C", os.path.join(os.path.dirname(HERE), "..", "oracle"), "ref_debug"], check=True,
+                   capture_output=True)
+    oracle_py._REF_LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle", "_ref", "libref_debug.so")
+    oracle_py._ref_lib = None
+    ok = True
+    for name in sorted(os.listdir(HERE)):
+        if not (name.startswith("ref_") and name.endswith(".npz")):
+            continue
+        g = np.load(os.path.join(HERE, name))
+        with oracle_py.using_ref():
+            if "x0" in g.files:
+                T = g["controls"].shape[1]
+                sp = g["set_points"] if "set_points" in g.files else np.zeros(g["x0"].shape[0])
+                nt = 1 if g["x0"].shape[0] == 1 else 0
+                _, ctl, _, counts, _, _ = oracle_py.closed_loop(g["opt"], g["x0"], g["dyn"], sp, T, n_threads=nt)
+                same = np.array_equal(ctl, g["controls"]) and np.array_equal(counts, g["counts"])
+            else:
+                w = g["weights"] if g["weights"].size else None
+                r = oracle_py.batch_step(g["opt"], g["states"], g["dyn"], g["set_points"], weights=w)
+                same = np.array_equal(r.u, g["u"]) and np.array_equal(r.stats, g["stats"])
+        print(f"{name}: {'bit-identical' if same else 'DIFFERENT'}")
+        ok = ok and same
+    return 0 if ok else 1
+
+
 if __name__ == "__main__":
+    if "--check-debug" in sys.argv:
+        sys.exit(check_debug())
     main()
