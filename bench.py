@@ -49,7 +49,23 @@ def algorithmic_flops(n_iter, n_ls, W=40, S=10, n_te=3, n_cost=81, nx=4, C_f=76,
     return n_iter * (F_lin + F_qp + F_dir) + n_ls * F_merit + 2 * F_roll
 
 
-NCU_SUMMARY = "profiles/r01_l_final.json"
+NCU_SUMMARY = "profiles/r02_final.json"
+
+
+def headline_config(B, allgather=False):
+    """`config` of the bench line, IDENTICAL in both arms (--impl ours / reference): it names the workload, not the
+    implementation."""
+    return {"workload": f"{B}-instance batched cold-start swing-up solves per GPU, W=40 S=10 max_iter=8, "
+                        "randomized initial states and cart/pole masses (BASELINE.json configs[1])",
+            "batch_per_gpu": B, "l2": "flushed between timed steps (256 MiB write, untimed)",
+            "outputs": "u, predicted_states and solver stats all computed every step",
+            "allgather": bool(allgather)}
+
+
+def env_knobs():
+    """Experiment switches of libcpmpc.so (csrc/cpmpc_capi.cu) that were set for this run: they change the mapping and
+    with it the rounding, so the line records them."""
+    return {k: v for k, v in sorted(os.environ.items()) if k.startswith("CPMPC_")}
 
 
 def ncu_dram_traffic(batch):
@@ -191,7 +207,9 @@ def cpu_baseline(states, dyn, sp, repeats=3, n_threads=0, prefer_ref=True):
 
 def run_reference(args):
     """--impl reference: the reference's CPU implementation on the host cores (oracle/_ref when built, else the
-    oracle port), same metric and config."""
+    oracle port), same metric and config.  Exactly --warmup untimed and --steps timed steps; a step is the full batch
+    when K of them fit in about two minutes on this host, else a bounded prefix of the same seeded batch (stated in
+    cpu_baseline.sample)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -200,30 +218,36 @@ def run_reference(args):
     B = args.batch
     states, dyn, sp = synthetic.swingup_batch(B)
     opt = oracle_py.opt_array()
-    threads = 0
+    threads = host_threads()
     ctx, kind = cpu_impl()
     times = []
     res = None
     with ctx():
+        # rate probe (untimed): sizes the per-step sample
+        n_probe = min(B, 512)
+        t0 = time.perf_counter()
+        oracle_py.batch_step(opt, states[:n_probe], dyn[:n_probe], sp[:n_probe], want_iter_log=False, n_threads=threads)
+        rate = n_probe / (time.perf_counter() - t0)
+        budget_s = 120.0
+        n_s = B if B * (args.steps + args.warmup) / rate <= budget_s else \
+            int(max(256, min(B, budget_s * rate / (args.steps + args.warmup))))
         for _ in range(args.warmup):
-            threads = oracle_py.batch_step(opt, states[:256], dyn[:256], sp[:256], want_iter_log=False,
-                                           n_threads=host_threads()).threads
+            oracle_py.batch_step(opt, states[:n_s], dyn[:n_s], sp[:n_s], want_iter_log=False, n_threads=threads)
         for _ in range(args.steps):
             t0 = time.perf_counter()
-            res = oracle_py.batch_step(opt, states, dyn, sp, want_iter_log=False, n_threads=host_threads())
+            res = oracle_py.batch_step(opt, states[:n_s], dyn[:n_s], sp[:n_s], want_iter_log=False, n_threads=threads)
             times.append(time.perf_counter() - t0)
             threads = res.threads
     total = float(np.sum(times))
-    value = B * args.steps / total
+    value = n_s * args.steps / total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{B}-instance batched cold-start swing-up solves, W=40 S=10 max_iter=8, randomized "
-                               "initial states and cart/pole masses (BASELINE.json configs[1]); CPU, one instance "
-                               "per thread"},
+        "config": headline_config(B, getattr(args, "allgather", False)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
-                         "sample": f"{B} instances x {args.steps} passes (the full step workload)",
+                         "sample": (f"{n_s} of the {B} instances per step" if n_s < B else f"all {B} instances per step")
+                                   + f", {args.steps} timed steps, one instance per thread",
                          "note": REF_NOTE if kind == "reference" else "oracle restatement (oracle/_ref not built)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -244,9 +268,22 @@ def _dist_setup():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        if not dist.is_initialized():  # the default line embeds these workloads after its own set-up
+            dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     return world, rank, local_rank, dist, torch.device("cuda", local_rank)
+
+
+def _finish(line, dist, embedded):
+    """Stand-alone (--workload configN): rank 0 prints the line and the process group is torn down.  Embedded in the
+    default line (`other_configs`): the dict is returned to the caller on rank 0, None elsewhere."""
+    if embedded:
+        return line
+    if line is not None:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
 
 
 def _max_over_ranks(dist, dev, values):
@@ -267,7 +304,7 @@ def _sum_over_ranks(dist, dev, values):
     return [float(v) for v in t]
 
 
-def run_closed_loop(args):
+def run_closed_loop(args, embedded=False):
     """configs[2]: receding-horizon MPC, B plants x n control steps, warm-started solves, plant integrated on the
     device between solves (one launch for the whole loop).  A "step" of the bench = the whole closed loop."""
     import torch
@@ -323,9 +360,8 @@ def run_closed_loop(args):
     (total_ms, e2e_s) = _max_over_ranks(dist, dev, [total_ms, e2e_s])
     (solves_all, flops_all) = _sum_over_ranks(dist, dev, [counts[0], flops])
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return 0
+        solver.close()
+        return _finish(None, dist, embedded)
     peak = measure_fp64_peak(local_rank)
     per_loop_ms = total_ms / steps
     line = {
@@ -358,16 +394,36 @@ def run_closed_loop(args):
         # closed-loop parity on the sample: applied controls of the first ticks (before chaos separates trajectories)
         d = np.abs(ctl[:nb, :nt] - ctl_o)
         line["cpu_baseline"]["bad_terminations_in_sample"] = int(cnt_o[3])
-        line["parity"] = {"median_abs_du_first_tick": float(np.median(d[:, 0])),
-                          "frac_plants_all_ticks_within_1e-6": float((d.max(axis=1) <= 1e-6).mean()),
-                          "frac_ticks_within_1e-8": float((d <= 1e-8).mean())}
-    print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
-    return 0
+        line["parity_free_running"] = {"median_abs_du_first_tick": float(np.median(d[:, 0])),
+                                       "frac_plants_all_ticks_within_1e-6": float((d.max(axis=1) <= 1e-6).mean()),
+                                       "frac_ticks_within_1e-8": float((d <= 1e-8).mean()),
+                                       "note": "free-running trajectories: solver disagreement and chaotic divergence "
+                                               "of an unstable plant are not separated here; `parity` is"}
+        if kind == "reference":
+            # teacher-forced: every tick of the reference's own closed loop re-solved by the GPU from the reference's
+            # plant state and warm start, one solve compared with one solve (tests/parity_diagnose.py)
+            np_, nt_ = 64, min(T, 50)
+            tr = oracle_py.closed_loop_trace(oracle_py.opt_array(**over), st_h[:np_], dy_h[:np_], sp_h[:np_], nt_,
+                                             n_threads=host_threads())
+            nb_ = np_ * nt_
+            tf = BatchedOptimization(nb_, device=local_rank, **over)
+            tf.set_previous_solution(tr.prev.reshape(nb_, -1), mask=np.tile((np.arange(nt_) > 0).astype(np.uint8), np_))
+            o_tf = tf.step(tr.states.reshape(nb_, 4), np.repeat(dy_h[:np_], nt_, axis=0), np.repeat(sp_h[:np_], nt_))
+            tf.close()
+            rs = tr.stats.reshape(nb_, -1)
+            m_ref = rs[:, 3] + rs[:, 5] * rs[:, 4]
+            rel = np.abs(o_tf.merit - m_ref) / np.maximum(np.abs(m_ref), 1e-300)
+            line["parity"] = {"frac_within_1e-8_rel_cost": float((rel <= 1e-8).mean()),
+                              "iteration_count_match": float((o_tf.stats["n_iterations"] == rs[:, 1].astype(int)).mean()),
+                              "termination_match": float((o_tf.stats["termination_state"] == rs[:, 0].astype(int)).mean()),
+                              "against": "compiled reference (oracle/_ref), teacher-forced closed loop",
+                              "sample": f"{np_} plants x {nt_} ticks, each tick solved from the reference's state and "
+                                        "warm start"}
+    solver.close()
+    return _finish(line, dist, embedded)
 
 
-def run_sweep(args):
+def run_sweep(args, embedded=False):
     """configs[3]: parameter / cost-weight sweep with a 4x horizon (W=160, S=10), 1M instances over 8 GPUs
     = 131072 per GPU, cold start."""
     import torch
@@ -413,9 +469,8 @@ def run_sweep(args):
     (total_ms,) = _max_over_ranks(dist, dev, [total_ms])
     (flops_all,) = _sum_over_ranks(dist, dev, [flops])
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return 0
+        solver.close()
+        return _finish(None, dist, embedded)
     peak = measure_fp64_peak(local_rank)
     ms = total_ms / steps
     hist = np.bincount(np.maximum(stats["termination_state"], 0), minlength=7).tolist()
@@ -448,14 +503,16 @@ def run_sweep(args):
         rel = np.abs(g - ora.merit) / np.maximum(np.abs(ora.merit), 1e-300)
         line["parity"] = {"frac_within_1e-8_rel_cost": float((rel <= 1e-8).mean()),
                           "iteration_count_match": float((stats["n_iterations"][:nb] == ora.n_iterations).mean()),
-                          "termination_match": float((stats["termination_state"][:nb] == ora.termination).mean())}
-    print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
-    return 0
+                          "termination_match": float((stats["termination_state"][:nb] == ora.termination).mean()),
+                          "against": "compiled reference (oracle/_ref)" if kind == "reference" else "oracle restatement",
+                          "sample": f"the first {nb} instances",
+                          "cpu_vs_cpu_floor": "two CPU implementations of the reference algorithm agree on 96.1 % of "
+                                              "these solves at 1e-8 (profiles/r02_parity_floor.json)"}
+    solver.close()
+    return _finish(line, dist, embedded)
 
 
-def run_double(args):
+def run_double(args, embedded=False):
     """configs[4]: double pendulum on a cart (nx=6), 262144 instances in total (strong scaling: 262144 / N per GPU),
     cold start, through the plant-generic kernels (csrc/plant_solver_kernel.cuh)."""
     import torch
@@ -504,9 +561,8 @@ def run_double(args):
     (total_ms,) = _max_over_ranks(dist, dev, [total_ms])
     (flops_all,) = _sum_over_ranks(dist, dev, [flops])
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return 0
+        solver.close()
+        return _finish(None, dist, embedded)
     peak = measure_fp64_peak(local_rank)
     ms = total_ms / steps
     hist = np.bincount(np.maximum(stats["termination_state"], 0), minlength=7).tolist()
@@ -542,10 +598,8 @@ def run_double(args):
         line["parity"] = {"frac_within_1e-8_rel_cost": float((rel <= 1e-8).mean()),
                           "iteration_count_match": float((stats["n_iterations"][:nb] == ora.n_iterations).mean()),
                           "termination_match": float((stats["termination_state"][:nb] == ora.termination).mean())}
-    print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
-    return 0
+    solver.close()
+    return _finish(line, dist, embedded)
 
 
 def main():
@@ -562,6 +616,8 @@ def main():
                     help="config2: the headline bench (default); config3: closed loop; config4: long-horizon sweep; config5: double pendulum on a cart")
     ap.add_argument("--cl-steps", type=int, default=500, help="control steps of the closed loop (config3)")
     ap.add_argument("--test-variant", action="store_true", help="config3 with optimization_test.cc's S=5, max_iter=10")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="default line only: skip the embedded configs[2..4] block (`other_configs`)")
     args = ap.parse_args()
     if args.impl != "reference" and args.workload == "config3":
         return run_closed_loop(args)
@@ -571,10 +627,6 @@ def main():
         return run_double(args)
 
     if args.impl == "reference":
-        if args.steps > 20:
-            args.steps = 20  # bounded so the CPU arm ends within a couple of minutes
-        if args.warmup > 3:
-            args.warmup = 3
         return run_reference(args)
 
     import torch
@@ -726,16 +778,25 @@ def main():
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         mask = sum(1 << i for i, nm in enumerate(names) if nm in clocks["reasons"])
         lm_iters = float(((stats["lambda"] > 0) | (stats["n_failed_line_searches"] > 0)).sum())
+        # what names a straggler: the slowest WARP of this rank's launch (SM cycles, clock64) against its median warp,
+        # and the hardest instance's failed line searches (each one is followed by a Levenberg-Marquardt iteration)
+        wc = solver.warp_cycles().astype(np.float64)
+        wc = wc[wc > 0]
         mine = torch.tensor([total_ms / args.steps, float(np.median(step_ms)), float(step_ms.max()),
-                             clocks["sm_mhz"] or 0.0, float(mask), float(stats["n_line_search_steps"].max()), lm_iters],
+                             clocks["sm_mhz"] or 0.0, float(mask), float(stats["n_line_search_steps"].max()), lm_iters,
+                             float(wc.max()) if wc.size else 0.0, float(np.median(wc)) if wc.size else 0.0,
+                             float(stats["n_failed_line_searches"].max())],
                             dtype=torch.float64, device=dev)
-        allr = torch.empty((world, 7), dtype=torch.float64, device=dev)
+        allr = torch.empty((world, 10), dtype=torch.float64, device=dev)
         dist.all_gather_into_tensor(allr, mine)
         per_rank = {"mean_step_ms": [float(v) for v in allr[:, 0]], "median_step_ms": [float(v) for v in allr[:, 1]],
                     "max_step_ms": [float(v) for v in allr[:, 2]], "sm_mhz": [float(v) for v in allr[:, 3]],
                     "throttle_reasons": [[nm for i, nm in enumerate(names) if int(v) >> i & 1] for v in allr[:, 4]],
                     "max_merit_evaluations_of_one_instance": [int(v) for v in allr[:, 5]],
                     "instances_with_failed_line_search_or_lm_damping": [int(v) for v in allr[:, 6]],
+                    "slowest_warp_kcycles": [round(float(v) / 1e3, 1) for v in allr[:, 7]],
+                    "median_warp_kcycles": [round(float(v) / 1e3, 1) for v in allr[:, 8]],
+                    "max_failed_line_searches_of_one_instance": [int(v) for v in allr[:, 9]],
                     "note": "each rank owns different instances and 4096 instances are ONE wave of warps, so a "
                             "rank's step time is the latency of its hardest warp; the max over ranks is reported"}
         all_reasons = sorted({r for rs in per_rank["throttle_reasons"] for r in rs})
@@ -748,6 +809,29 @@ def main():
         flops_step_all = float(w[0])
     else:
         flops_step_all = flops_step
+        wc = solver.warp_cycles().astype(np.float64)
+        wc = wc[wc > 0]
+
+    # ---- BASELINE.json configs[2..4] in the same line (`other_configs`): every rank takes part (their timing uses
+    # collectives), rank 0 keeps the result.  Bounded sizes so the default run still ends within a couple of minutes.
+    other = None
+    if B == DEFAULT_BATCH and not args.no_other_configs:
+        del flush
+        torch.cuda.empty_cache()
+        sub = argparse.Namespace(**vars(args))
+        sub.batch, sub.steps, sub.warmup, sub.cl_steps, sub.test_variant = DEFAULT_BATCH, 2, 1, 50, False
+        other = {}
+        for name, fn in (("config3_closed_loop", run_closed_loop), ("config4_long_horizon_sweep", run_sweep),
+                         ("config5_double_pendulum", run_double)):
+            try:
+                res_o = fn(sub, embedded=True)
+            except Exception as exc:  # supplementary: never lose the headline line over it
+                res_o = {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}
+            if res_o is not None:
+                keep = ("metric", "value", "unit", "n_gpus", "steps", "ms_per_step", "scaling", "config", "e2e", "clocks",
+                        "roofline", "parity", "parity_free_running", "cpu_baseline", "mean_sqp_iterations",
+                        "mean_merit_evaluations", "bad_terminations", "termination_hist", "error")
+                other[name] = {k: res_o[k] for k in keep if k in res_o}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -771,11 +855,8 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"{B}-instance batched cold-start swing-up solves per GPU, W=40 S=10 max_iter=8, "
-                               "randomized initial states and cart/pole masses (BASELINE.json configs[1])",
-                   "batch_per_gpu": B, "l2": "flushed between timed steps (256 MiB write, untimed)",
-                   "outputs": "u, predicted_states and solver stats all computed every step",
-                   "allgather": bool(gathered_u is not None)},
+        "config": headline_config(B, gathered_u is not None),
+        "env_knobs": env_knobs(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "path": "cpmpc_step: pinned host buffers -> H2D -> kernel -> D2H"},
         "gpu_launches": int(launches),
@@ -799,6 +880,9 @@ def main():
         "aggregate_algorithmic_tflops": flops_step_all / (kernel_ms * 1e-3) / 1e12,
     }
 
+    if other:
+        line["other_configs"] = other
+    line["warp_kcycles_max_median"] = [round(float(wc.max()) / 1e3, 1), round(float(np.median(wc)) / 1e3, 1)] if wc.size else None
     if per_rank is not None:
         line["per_rank"] = per_rank
     if world == 1 and B == DEFAULT_BATCH and not args.no_cpu_baseline:

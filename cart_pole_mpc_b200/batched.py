@@ -176,6 +176,41 @@ class BatchedOptimization:
         _capi.check(self._lib.cpmpc_get_previous_solution(self._h, sol.ctypes.data, has.ctypes.data))
         return sol, has.astype(bool)
 
+    def warp_cycles(self) -> np.ndarray:
+        """SM cycles every warp of the last launch spent on its instances (cpmpc_get_warp_cycles)."""
+        n = int(self._lib.cpmpc_get_warp_cycles(self._h, None, 0))
+        out = np.zeros(max(n, 0), dtype=np.uint64)
+        if n > 0 and self._lib.cpmpc_get_warp_cycles(self._h, out.ctypes.data, n) != n:
+            raise _capi.CpmpcError("cpmpc_get_warp_cycles failed")
+        return out
+
+    # ---- debug view inside the first SQP iteration ----------------------------------------------------------------
+    def debug_first_qp(self, states, dyn_params, set_points, weights=None, lam: float = 0.0, qp_method: int = 0):
+        """Blocks of the first linearisation and its QP step (cpmpc_debug_first_qp): a dict of arrays
+        Phi [B,nseg,4,4], Gam [B,4,W], e [B,nseg,4], dxs [B,NS,4], du [B,W], qp_ok [B], f0 [B], eq0 [B].
+        The warm start is honoured and left untouched."""
+        B, W = self.batch, self.W
+        nseg = W // self.S
+        NS = nseg + 1
+        st = _host(states, (B, 4), "states")
+        dyn = _host(dyn_params, (B, 9), "dyn_params")
+        sp = _host(set_points, (B,), "set_points")
+        wts = _host(weights, (B, _capi.WEIGHTS_STRIDE), "weights") if weights is not None else None
+        stride = int(self._lib.cpmpc_debug_stride(self._h))
+        raw = np.empty((B, stride), dtype=np.float64)
+        _capi.check(self._lib.cpmpc_debug_first_qp(
+            self._h, st.ctypes.data, dyn.ctypes.data, sp.ctypes.data, wts.ctypes.data if wts is not None else None,
+            float(lam), int(qp_method), raw.ctypes.data))
+        o = 0
+        out = {}
+        for name, shape in (("Phi", (nseg, 4, 4)), ("Gam", (4, W)), ("e", (nseg, 4)), ("dxs", (NS, 4)), ("du", (W,))):
+            n = int(np.prod(shape))
+            out[name] = raw[:, o:o + n].reshape((B,) + shape)
+            o += n
+        out["qp_ok"] = raw[:, o] != 0.0
+        out["f0"], out["eq0"], out["lambda"] = raw[:, o + 1], raw[:, o + 2], raw[:, o + 3]
+        return out
+
     # ---- per-iteration log ----------------------------------------------------------------------------------------
     def enable_iteration_log(self, enable: bool = True) -> None:
         _capi.check(self._lib.cpmpc_enable_iteration_log(self._h, 1 if enable else 0))

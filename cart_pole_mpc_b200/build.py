@@ -72,5 +72,38 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+NATIVE_DIR = os.path.join(PKG_DIR, "native")
+PYPENDULUM_SRC = os.path.join(PKG_DIR, "host", "pypendulum_ext.cc")
+
+
+def pypendulum_path() -> str:
+    import sysconfig
+    return os.path.join(NATIVE_DIR, "pypendulum" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_pypendulum(force: bool = False) -> str:
+    """Compile the native `pypendulum` module (pybind11 over host/optimization.hpp, the binding list of the reference's
+    wrapper/wrapper.cc:40-102) into cart_pole_mpc_b200/native/.  g++ only; it links libcpmpc.so by relative rpath."""
+    import sysconfig
+    import pybind11
+    out = pypendulum_path()
+    deps = [PYPENDULUM_SRC, os.path.join(PKG_DIR, "host", "optimization.hpp"), os.path.join(PKG_DIR, "host", "structs.hpp"),
+            os.path.join(PKG_DIR, "..", "include", "cpmpc.h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) > os.path.getmtime(d) for d in deps):
+        return out
+    build_library()
+    os.makedirs(NATIVE_DIR, exist_ok=True)
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden", "-I" + pybind11.get_include(),
+           "-I" + sysconfig.get_paths()["include"], "-o", out, PYPENDULUM_SRC, "-L" + PKG_DIR, "-lcpmpc",
+           "-Wl,-rpath,$ORIGIN/.."]
+    proc = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if proc.returncode != 0:
+        raise RuntimeError("building pypendulum failed:\n" + proc.stdout + proc.stderr)
+    return out
+
+
 if __name__ == "__main__":
     print(build_library(force=True, verbose=True))
+    print(build_pypendulum(force=True))

@@ -67,6 +67,7 @@ struct cpmpc_solver {
   unsigned long long* d_queue = nullptr;
   double* d_iter_log = nullptr;
   bool log_enabled = false;
+  unsigned long long* d_warp_cycles = nullptr;  // [grid * warps_per_block] per-warp SM cycles of the last launch
   // staging for the host-buffer entry points
   double* d_states = nullptr;
   double* d_dyn = nullptr;
@@ -81,6 +82,9 @@ struct cpmpc_solver {
   // small batches: one packed pinned host buffer and its device twin, so that a Step() costs one copy each way
   unsigned char* h_pack = nullptr;
   unsigned char* d_pack = nullptr;
+  // cpmpc_reset_device runs on the caller's stream; the host-buffer entry points run on `stream` and wait for it
+  cudaEvent_t reset_event = nullptr;
+  bool reset_pending = false;
 };
 
 namespace {
@@ -146,24 +150,48 @@ int Launch(cpmpc_solver* h, KernelIO io, cudaStream_t stream) {
   io.kk_scratch = h->d_kk;
   io.queue = h->d_queue;
   io.iter_log = h->log_enabled ? h->d_iter_log : nullptr;
+  io.warp_cycles = h->d_warp_cycles;
   fn<<<h->grid, 32 * h->warps_per_block, h->smem_bytes, stream>>>(h->cfg, io);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return CPMPC_OK;
 }
 
+// Staging buffers of the host-buffer entry points: allocated together on first use, all or nothing.
 int EnsureStaging(cpmpc_solver* h) {
-  if (h->d_states != nullptr) return CPMPC_OK;
+  if (h->d_stats_sum != nullptr) return CPMPC_OK;  // the last one allocated
   const long long B = h->B;
   const int W = h->cfg.W;
-  CUDA_TRY(cudaMalloc(&h->d_states, sizeof(double) * B * 4));
-  CUDA_TRY(cudaMalloc(&h->d_dyn, sizeof(double) * B * 9));
-  CUDA_TRY(cudaMalloc(&h->d_sp, sizeof(double) * B));
-  CUDA_TRY(cudaMalloc(&h->d_weights, sizeof(double) * B * CPMPC_WEIGHTS_STRIDE));
-  CUDA_TRY(cudaMalloc(&h->d_u, sizeof(double) * B * W));
-  CUDA_TRY(cudaMalloc(&h->d_pred, sizeof(double) * B * W * 4));
-  CUDA_TRY(cudaMalloc(&h->d_stats, sizeof(cpmpc_stats) * B));
-  CUDA_TRY(cudaMalloc(&h->d_stats_sum, sizeof(long long) * 4));
+  auto alloc_all = [&]() -> int {
+    CUDA_TRY(cudaMalloc(&h->d_states, sizeof(double) * B * 4));
+    CUDA_TRY(cudaMalloc(&h->d_dyn, sizeof(double) * B * 9));
+    CUDA_TRY(cudaMalloc(&h->d_sp, sizeof(double) * B));
+    CUDA_TRY(cudaMalloc(&h->d_weights, sizeof(double) * B * CPMPC_WEIGHTS_STRIDE));
+    CUDA_TRY(cudaMalloc(&h->d_u, sizeof(double) * B * W));
+    CUDA_TRY(cudaMalloc(&h->d_pred, sizeof(double) * B * W * 4));
+    CUDA_TRY(cudaMalloc(&h->d_stats, sizeof(cpmpc_stats) * B));
+    CUDA_TRY(cudaMalloc(&h->d_stats_sum, sizeof(long long) * 4));
+    return CPMPC_OK;
+  };
+  const int rc = alloc_all();
+  if (rc != CPMPC_OK) {
+    for (void** p : {reinterpret_cast<void**>(&h->d_states), reinterpret_cast<void**>(&h->d_dyn),
+                     reinterpret_cast<void**>(&h->d_sp), reinterpret_cast<void**>(&h->d_weights),
+                     reinterpret_cast<void**>(&h->d_u), reinterpret_cast<void**>(&h->d_pred),
+                     reinterpret_cast<void**>(&h->d_stats), reinterpret_cast<void**>(&h->d_stats_sum)}) {
+      cudaFree(*p);
+      *p = nullptr;
+    }
+  }
+  return rc;
+}
+
+// Orders the handle's own stream behind a cpmpc_reset_device issued on another stream.
+int WaitForReset(cpmpc_solver* h) {
+  if (h->reset_pending) {
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, h->reset_event, 0));
+    h->reset_pending = false;
+  }
   return CPMPC_OK;
 }
 
@@ -278,6 +306,13 @@ int cpmpc_create_ex(const cpmpc_params* params, int64_t batch, int device, uint3
   CUDA_TRY(cudaSetDevice(device));
 
   cpmpc_solver* h = new cpmpc_solver();
+  // any failure below releases the handle and whatever it already owns
+  struct Guard {
+    cpmpc_solver* h;
+    ~Guard() {
+      if (h != nullptr) cpmpc_destroy(h);
+    }
+  } guard{h};
   h->params = *params;
   h->B = batch;
   h->device = device;
@@ -368,7 +403,6 @@ int cpmpc_create_ex(const cpmpc_params* params, int64_t batch, int device, uint3
   h->lanes = lanes;
   const int groups_per_warp = 32 / lanes;
   if (smem_per_warp > static_cast<size_t>(prop.sharedMemPerBlockOptin)) {
-    delete h;
     return Fail(CPMPC_ERR_UNSUPPORTED, "problem needs " + std::to_string(smem_per_warp) +
                                            " bytes of shared memory per warp, device offers " +
                                            std::to_string(prop.sharedMemPerBlockOptin));
@@ -390,11 +424,14 @@ int cpmpc_create_ex(const cpmpc_params* params, int64_t batch, int device, uint3
   h->warps_per_block = wpb;
   h->smem_bytes = smem_per_warp * wpb;
   KernelFn fn = SelectKernel(lanes);
-  CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->smem_bytes)));
+  // The attribute belongs to the kernel instantiation (per device), not to the handle: handles that share an
+  // instantiation but differ in warps per block must not lower each other's limit, so it is always set to the
+  // device maximum.
+  CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(prop.sharedMemPerBlockOptin)));
   int blocks_per_sm = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, 32 * wpb, h->smem_bytes));
   if (blocks_per_sm < 1) {
-    delete h;
     return Fail(CPMPC_ERR_UNSUPPORTED, "kernel does not fit on an SM");
   }
   const long long groups_per_block = static_cast<long long>(groups_per_warp) * wpb;
@@ -408,6 +445,8 @@ int cpmpc_create_ex(const cpmpc_params* params, int64_t batch, int device, uint3
   CUDA_TRY(cudaMemset(h->d_has_prev, 0, batch));
   CUDA_TRY(cudaMemset(h->d_prev, 0, sizeof(double) * batch * k.N));
   CUDA_TRY(cudaMalloc(&h->d_kk, sizeof(double) * n_groups * k.kk_stride));
+  CUDA_TRY(cudaMalloc(&h->d_warp_cycles, sizeof(unsigned long long) * h->grid * wpb));
+  CUDA_TRY(cudaMemset(h->d_warp_cycles, 0, sizeof(unsigned long long) * h->grid * wpb));
   CUDA_TRY(cudaMalloc(&h->d_queue, sizeof(unsigned long long) * 2));
   CUDA_TRY(cudaMemset(h->d_queue, 0, sizeof(unsigned long long) * 2));
   CUDA_TRY(cudaMalloc(&h->d_u_guess, sizeof(double) * k.W));
@@ -419,6 +458,8 @@ int cpmpc_create_ex(const cpmpc_params* params, int64_t batch, int device, uint3
   }
   CUDA_TRY(cudaMemcpy(h->d_u_guess, guess.data(), sizeof(double) * k.W, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&h->reset_event, cudaEventDisableTiming));
+  guard.h = nullptr;
   *out = h;
   return CPMPC_OK;
 }
@@ -431,6 +472,7 @@ int cpmpc_destroy(cpmpc_handle h) {
   cudaFree(h->d_u_guess);
   cudaFree(h->d_kk);
   cudaFree(h->d_queue);
+  cudaFree(h->d_warp_cycles);
   cudaFree(h->d_iter_log);
   cudaFree(h->d_states);
   cudaFree(h->d_dyn);
@@ -443,6 +485,7 @@ int cpmpc_destroy(cpmpc_handle h) {
   cudaFree(h->d_controls);
   cudaFree(h->d_pack);
   if (h->h_pack) cudaFreeHost(h->h_pack);
+  if (h->reset_event) cudaEventDestroy(h->reset_event);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return CPMPC_OK;
@@ -480,6 +523,7 @@ int cpmpc_step(cpmpc_handle h, const double* states, const double* dyn_params, c
     return Fail(CPMPC_ERR_INVALID_ARGUMENT, "states, dyn_params, set_points and u_out are required");
   }
   CUDA_TRY(cudaSetDevice(h->device));
+  if (int rc = WaitForReset(h)) return rc;
   if (h->B <= kPackedBatchMax) return StepPacked(h, states, dyn_params, set_points, weights, u_out, pred_out, stats_out);
   if (int rc = EnsureStaging(h)) return rc;
   const long long B = h->B;
@@ -528,6 +572,9 @@ int cpmpc_reset_device(cpmpc_handle h, void* stream) {
   if (h == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "null handle");
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaMemsetAsync(h->d_has_prev, 0, h->B, static_cast<cudaStream_t>(stream)));
+  // the host-buffer entry points run on the handle's own (non-blocking) stream: they wait for this event
+  CUDA_TRY(cudaEventRecord(h->reset_event, static_cast<cudaStream_t>(stream)));
+  h->reset_pending = true;
   return CPMPC_OK;
 }
 
@@ -592,6 +639,7 @@ int cpmpc_sim_step_device(int64_t batch, double* states, const double* dyn_param
     return Fail(CPMPC_ERR_INVALID_ARGUMENT, "batch, states, dyn_params and u are required");
   }
   if (!(dt >= 0.0)) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "dt must be >= 0");  // simulator.cc:13
+  // runs on the CURRENT device of the calling thread: the pointers decide where the data lives
   const int threads = 128;
   const long long blocks = (batch + threads - 1) / threads;
   cpmpc_sim_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -611,25 +659,26 @@ int cpmpc_sim_step(int device, int64_t batch, double* states, const double* dyn_
   }
   CUDA_TRY(cudaSetDevice(device));
   double *d_s = nullptr, *d_d = nullptr, *d_u = nullptr, *d_fb = nullptr, *d_fm = nullptr;
-  CUDA_TRY(cudaMalloc(&d_s, sizeof(double) * batch * 4));
-  CUDA_TRY(cudaMalloc(&d_d, sizeof(double) * batch * 9));
-  CUDA_TRY(cudaMalloc(&d_u, sizeof(double) * batch));
-  CUDA_TRY(cudaMemcpy(d_s, states, sizeof(double) * batch * 4, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(d_d, dyn_params, sizeof(double) * batch * 9, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(d_u, u, sizeof(double) * batch, cudaMemcpyHostToDevice));
-  if (f_base != nullptr) {
-    CUDA_TRY(cudaMalloc(&d_fb, sizeof(double) * batch * 2));
-    CUDA_TRY(cudaMemcpy(d_fb, f_base, sizeof(double) * batch * 2, cudaMemcpyHostToDevice));
-  }
-  if (f_mass != nullptr) {
-    CUDA_TRY(cudaMalloc(&d_fm, sizeof(double) * batch * 2));
-    CUDA_TRY(cudaMemcpy(d_fm, f_mass, sizeof(double) * batch * 2, cudaMemcpyHostToDevice));
-  }
-  int rc = cpmpc_sim_step_device(batch, d_s, d_d, d_u, dt, d_fb, d_fm, nullptr);
-  if (rc == CPMPC_OK) {
-    const cudaError_t e = cudaMemcpy(states, d_s, sizeof(double) * batch * 4, cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) rc = Fail(CPMPC_ERR_CUDA, cudaGetErrorString(e));
-  }
+  auto run = [&]() -> int {
+    CUDA_TRY(cudaMalloc(&d_s, sizeof(double) * batch * 4));
+    CUDA_TRY(cudaMalloc(&d_d, sizeof(double) * batch * 9));
+    CUDA_TRY(cudaMalloc(&d_u, sizeof(double) * batch));
+    CUDA_TRY(cudaMemcpy(d_s, states, sizeof(double) * batch * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_d, dyn_params, sizeof(double) * batch * 9, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_u, u, sizeof(double) * batch, cudaMemcpyHostToDevice));
+    if (f_base != nullptr) {
+      CUDA_TRY(cudaMalloc(&d_fb, sizeof(double) * batch * 2));
+      CUDA_TRY(cudaMemcpy(d_fb, f_base, sizeof(double) * batch * 2, cudaMemcpyHostToDevice));
+    }
+    if (f_mass != nullptr) {
+      CUDA_TRY(cudaMalloc(&d_fm, sizeof(double) * batch * 2));
+      CUDA_TRY(cudaMemcpy(d_fm, f_mass, sizeof(double) * batch * 2, cudaMemcpyHostToDevice));
+    }
+    if (int rc = cpmpc_sim_step_device(batch, d_s, d_d, d_u, dt, d_fb, d_fm, nullptr)) return rc;
+    CUDA_TRY(cudaMemcpy(states, d_s, sizeof(double) * batch * 4, cudaMemcpyDeviceToHost));
+    return CPMPC_OK;
+  };
+  const int rc = run();  // temporaries are released on every path
   cudaFree(d_s);
   cudaFree(d_d);
   cudaFree(d_u);
@@ -668,6 +717,7 @@ int cpmpc_closed_loop(cpmpc_handle h, int64_t n_steps, double* states, const dou
     return Fail(CPMPC_ERR_INVALID_ARGUMENT, "n_steps >= 1, states, dyn_params and set_points are required");
   }
   CUDA_TRY(cudaSetDevice(h->device));
+  if (int rc = WaitForReset(h)) return rc;
   if (int rc = EnsureStaging(h)) return rc;
   const long long B = h->B;
   cudaStream_t s = h->stream;
@@ -699,6 +749,78 @@ int cpmpc_closed_loop(cpmpc_handle h, int64_t n_steps, double* states, const dou
   }
   CUDA_TRY(cudaStreamSynchronize(s));
   return CPMPC_OK;
+}
+
+int64_t cpmpc_get_warp_cycles(cpmpc_handle h, uint64_t* cycles_out, int64_t capacity) {
+  if (h == nullptr) return 0;
+  const int64_t n = static_cast<int64_t>(h->grid) * h->warps_per_block;
+  if (cycles_out == nullptr || capacity < n) return n;
+  if (cudaSetDevice(h->device) != cudaSuccess) return -1;
+  if (cudaMemcpy(cycles_out, h->d_warp_cycles, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    Fail(CPMPC_ERR_CUDA, "cudaMemcpy of the warp cycle counters failed");
+    return -1;
+  }
+  return n;
+}
+
+int64_t cpmpc_debug_stride(cpmpc_handle h) {
+  if (h == nullptr) return 0;
+  const KernelCfg& k = h->cfg;
+  return 16LL * k.nseg + 4LL * k.W + 4LL * k.nseg + 4LL * k.NS + k.W + 8;
+}
+
+int cpmpc_debug_first_qp(cpmpc_handle h, const double* states, const double* dyn_params, const double* set_points,
+                         const double* weights, double lambda, int qp_method, double* blocks_out) {
+  if (h == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "null handle");
+  if (states == nullptr || dyn_params == nullptr || set_points == nullptr || blocks_out == nullptr) {
+    return Fail(CPMPC_ERR_INVALID_ARGUMENT, "states, dyn_params, set_points and blocks_out are required");
+  }
+  if (!(lambda >= 0.0) || qp_method < 0 || qp_method > 2) {
+    return Fail(CPMPC_ERR_INVALID_ARGUMENT, "lambda must be >= 0 and qp_method one of 0, 1, 2");
+  }
+  if (qp_method == 2 && !h->cfg.condensed) {
+    return Fail(CPMPC_ERR_UNSUPPORTED, "this handle has no scratch for the condensed form (long horizon: W * dt > 0.6 s)");
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (int rc = WaitForReset(h)) return rc;
+  if (int rc = EnsureStaging(h)) return rc;
+  const long long B = h->B;
+  const long long stride = cpmpc_debug_stride(h);
+  cudaStream_t s = h->stream;
+  double* d_dbg = nullptr;
+  CUDA_TRY(cudaMalloc(&d_dbg, sizeof(double) * B * stride));
+  auto run = [&]() -> int {
+    CUDA_TRY(cudaMemsetAsync(d_dbg, 0, sizeof(double) * B * stride, s));
+    CUDA_TRY(cudaMemcpyAsync(h->d_states, states, sizeof(double) * B * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->d_dyn, dyn_params, sizeof(double) * B * 9, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->d_sp, set_points, sizeof(double) * B, cudaMemcpyHostToDevice, s));
+    if (weights != nullptr) {
+      CUDA_TRY(cudaMemcpyAsync(h->d_weights, weights, sizeof(double) * B * CPMPC_WEIGHTS_STRIDE,
+                               cudaMemcpyHostToDevice, s));
+    }
+    KernelIO io;
+    std::memset(&io, 0, sizeof(io));
+    io.states = h->d_states;
+    io.dyn = h->d_dyn;
+    io.set_points = h->d_sp;
+    io.weights = weights ? h->d_weights : nullptr;
+    io.n_steps = 1;
+    io.dbg = d_dbg;
+    io.dbg_stride = stride;
+    io.dbg_lambda = lambda;
+    io.dbg_qp = qp_method;
+    int rc = Launch(h, io, s);  // the kernel leaves the warm start alone when io.dbg is set
+    if (rc == CPMPC_OK) {
+      const cudaError_t e = cudaMemcpyAsync(blocks_out, d_dbg, sizeof(double) * B * stride, cudaMemcpyDeviceToHost, s);
+      if (e != cudaSuccess) rc = Fail(CPMPC_ERR_CUDA, cudaGetErrorString(e));
+    }
+    const cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess && rc == CPMPC_OK) rc = Fail(CPMPC_ERR_CUDA, cudaGetErrorString(e));
+    return rc;
+  };
+  const int rc = run();
+  cudaFree(d_dbg);
+  return rc;
 }
 
 int cpmpc_measure_fp64_peak(int device, double* tflops_out) {

@@ -279,8 +279,9 @@ int cpmpc_plant_create(int plant, const cpmpc_plant_params* params, int64_t batc
   h->warps_per_block = wpb;
   h->smem_bytes = smem_per_warp * wpb;
   KernelFn fn = SelectKernel(plant, lanes);
-  CPMPC_CUDA_TRY(
-      cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->smem_bytes)));
+  // per kernel instantiation and device, never lowered by a later handle (see cpmpc_capi.cu)
+  CPMPC_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(prop.sharedMemPerBlockOptin)));
   int blocks_per_sm = 0;
   CPMPC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, 32 * wpb, h->smem_bytes));
   if (blocks_per_sm < 1) {

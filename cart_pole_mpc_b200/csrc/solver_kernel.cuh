@@ -74,6 +74,15 @@ struct KernelIO {
   double* states_io;         // [B,4] in/out plant state when sim == 1
   double* controls_out;      // [B,n_steps] or nullptr
   long long* stats_sum;      // [4] or nullptr
+  // debug view of the first SQP iteration (cpmpc_debug_first_qp): when dbg != nullptr every instance linearises once,
+  // solves the QP with damping dbg_lambda, writes its blocks to dbg[inst * dbg_stride ...] and stops
+  double* dbg;               // [B, dbg_stride]: Phi [nseg*16] | Gam [4*W] | e [4*nseg] | dxs [4*NS] | du [W] | 8 scalars
+  long long dbg_stride;
+  double dbg_lambda;
+  int dbg_qp;                // 0: the handle's choice, 1: Riccati recursion, 2: condensed form
+  // [grid warps] SM cycles every warp spent between its first and its last instance (clock64), or nullptr: names
+  // the straggler warp of a launch (bench.py per_rank)
+  unsigned long long* warp_cycles;
 };
 
 // mini_opt enums (dependencies/mini_opt/include/mini_opt/structs.hpp:159-248), by declaration order.
@@ -979,7 +988,8 @@ struct SolveResult {
 template <int L>
 __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, const Weights& w,
                                             const double x_cur[4], const double& set_point, const double& u_prev,
-                                            double* iter_log, SolveResult& res) {
+                                            double* iter_log, SolveResult& res, double* dbg = nullptr,
+                                            const double dbg_lambda = 0.0, const int dbg_qp = 0) {
   const KernelCfg& k = *c.cfg;
   double* xs = c.sm + k.off_xs;
   double* u = c.sm + k.off_u;
@@ -1016,7 +1026,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
   bool& have_cur = cold.have_cur;
   bool& tri_valid = cold.tri_valid;
   active = active_in;
-  lambda = 0.0;  // params.lambda_initial (nonlinear.hpp:104)
+  lambda = (dbg != nullptr) ? dbg_lambda : 0.0;  // params.lambda_initial (nonlinear.hpp:104)
   penalty = k.pen_init;
   opt_state = OS_NOMINAL;
   cur_f = 0.0;
@@ -1202,23 +1212,87 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
       }
     }
 
+    // ---- QP step (qp.cc:679-729) ---------------------------------------------------------------------------------
+    double cdx = 0.0;
+    bool qp_ok = false;
+    bool need_riccati = false;
     if (active) {
-      // ---- QP step (qp.cc:679-729) -----------------------------------------------------------------------------
-      double cdx = 0.0;
-      bool qp_ok;
-      const bool try_condensed = k.condensed && !(lambda > 0.0);
-      qp_ok = false;
+      const bool try_condensed = (dbg != nullptr && dbg_qp != 0) ? (dbg_qp == 2) : (k.condensed && !(lambda > 0.0));
       if (try_condensed) {
         qp_ok = condensed_qp<L>(c, w, tri_valid, x_cur, target, cdx);
         // A failed 4x4 multiplier system is a property of the condensed formulation (open-loop sensitivity rows nearly
         // dependent), not necessarily of the QP: restore the gradient and let the Riccati recursion decide.
         if (!qp_ok) fill_gradient();
       }
-      if (!qp_ok) {
-        tri_valid = false;  // the Riccati stage matrix shares the scratch of the tridiagonal factor
-        qp_ok = riccati_qp<L>(c, w, lambda, x_cur, target, cdx);
+      need_riccati = !qp_ok && !(dbg != nullptr && dbg_qp == 2);
+      if (need_riccati) tri_valid = false;  // the Riccati stage matrix shares the scratch of the tridiagonal factor
+    }
+    if constexpr (L < 32 && L <= 4) {
+      // Narrow lane groups (short horizons) reach the Riccati recursion only for Levenberg-Marquardt iterations and as
+      // the fallback of the condensed form: a handful of instances per batch.  While one group runs it the other
+      // groups of the warp could only wait, so the WHOLE WARP works on that one instance instead (its blocks are in its
+      // own shared memory; the per-instance scalars are broadcast from its first lane): about 6 x shorter than L
+      // lanes on it alone.  This is what bounded the slowest rank of an 8-GPU run.
+      unsigned need_mask = __ballot_sync(0xffffffffu, need_riccati);
+      const int lane = (int)(threadIdx.x & 31);
+      const int g_mine = lane / L;
+      while (need_mask != 0u) {
+        const int src = __ffs(need_mask) - 1;  // first lane of the first group that needs it
+        const int g_src = src / L;
+        Weights wb;
+        wb.w_u = __shfl_sync(0xffffffffu, w.w_u, src);
+        wb.w_r = __shfl_sync(0xffffffffu, w.w_r, src);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wb.wt[i] = __shfl_sync(0xffffffffu, w.wt[i], src);
+        double xb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xb[i] = __shfl_sync(0xffffffffu, x_cur[i], src);
+        const double lam_b = __shfl_sync(0xffffffffu, lambda, src);
+        const double sp_b = __shfl_sync(0xffffffffu, set_point, src);
+        const double target_b[4] = {sp_b, half_pi, 0.0, 0.0};
+        Ctx cw;
+        cw.cfg = c.cfg;
+        cw.sm = c.sm + (ptrdiff_t)(g_src - g_mine) * k.stride;
+        cw.kk = c.kk + (ptrdiff_t)(g_src - g_mine) * k.kk_stride;
+        cw.gl = lane;
+        cw.gmask = 0xffffffffu;
+        double cdx_w = 0.0;
+        const bool ok_w = riccati_qp<32>(cw, wb, lam_b, xb, target_b, cdx_w);
+        cdx_w = group_sum<32>(cdx_w, 0xffffffffu);
+        if (g_mine == g_src) {
+          qp_ok = ok_w;
+          cdx = (c.gl == 0) ? cdx_w : 0.0;
+        }
+        need_mask &= ~((((L == 32) ? 0u : (1u << L)) - 1u) << (g_src * L));
+        __syncwarp(0xffffffffu);
       }
-      if (!qp_ok) {
+    } else {
+      if (need_riccati) qp_ok = riccati_qp<L>(c, w, lambda, x_cur, target, cdx);
+    }
+    if (active) {
+      if (dbg != nullptr) {
+        // debug view: the blocks of this linearisation and the QP step, then stop (the candidates would overwrite Gam)
+        CPMPC_GSYNC();
+        double* o = dbg;
+        for (int q = c.gl; q < 16 * nseg; q += L) o[q] = Phi[q];
+        o += 16 * nseg;
+        for (int q = c.gl; q < 4 * W; q += L) o[q] = Gam[q];
+        o += 4 * W;
+        for (int q = c.gl; q < 4 * nseg; q += L) o[q] = ev[q];
+        o += 4 * nseg;
+        for (int q = c.gl; q < 4 * NS; q += L) o[q] = dxs[q];
+        o += 4 * NS;
+        for (int q = c.gl; q < W; q += L) o[q] = du[q];
+        o += W;
+        if (c.gl == 0) {
+          o[0] = qp_ok ? 1.0 : 0.0;
+          o[1] = f0;
+          o[2] = eq0;
+          o[3] = lambda;
+        }
+        active = false;
+        qp_ok = true;
+      } else if (!qp_ok) {
         // QP_INDEFINITE: Solve() returns before this iteration is logged (nonlinear.cc:103-105)
         res.termination = TS_QP_INDEFINITE;
         active = false;
@@ -1455,6 +1529,7 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
   // Work queue: a warp takes G consecutive instances at a time, so warps that draw cheap instances (few line-search
   // trials) go on instead of idling until the slowest warp of a static round is done.  Warp-wide votes stay
   // convergent because all groups of a warp enter and leave a batch together.
+  const long long t_begin = clock64();
   for (;;) {
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(io.queue, (unsigned long long)G);
@@ -1556,18 +1631,24 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
       double* ilog = (io.iter_log != nullptr && have)
                          ? io.iter_log + (size_t)inst * cfg.max_iter * CPMPC_ITERLOG_STRIDE
                          : nullptr;
-      solve_group<L>(c, have, w, x_cur, set_point, u_prev, ilog, res);
+      double* dbg = (io.dbg != nullptr && have) ? io.dbg + (size_t)inst * io.dbg_stride : nullptr;
+      solve_group<L>(c, have, w, x_cur, set_point, u_prev, ilog, res, dbg, io.dbg_lambda, io.dbg_qp);
 
       if (have) {
         // ---- outputs (optimization.cc:83-96) ------------------------------------------------------------------
+        // A rejected instance keeps its previous warm start: the reference throws inside Solve()
+        // (nonlinear.cc:356-357) before previous_solution_ is assigned (optimization.cc:84-85).  The debug view
+        // never touches the warm start either.
+        const bool keep = res.termination != TS_REJECTED && io.dbg == nullptr;
         double* prev = io.prev + inst * N;
-        for (int q = c.gl; q < 4 * NS; q += L) prev[q] = xs[q];
+        if (keep)
+          for (int q = c.gl; q < 4 * NS; q += L) prev[q] = xs[q];
         for (int q = c.gl; q < W; q += L) {
-          prev[4 * NS + q] = u[q];
+          if (keep) prev[4 * NS + q] = u[q];
           if (io.u_out != nullptr) io.u_out[inst * W + q] = u[q];
         }
         if (c.gl == 0) {
-          io.has_prev[inst] = 1;
+          if (keep) io.has_prev[inst] = 1;
           if (io.pred_out != nullptr) {
             // ComputePredictedStates (optimization.cc:353-371)
             DynConst Pl;
@@ -1647,6 +1728,9 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
   }
   // the last warp to drain the queue re-arms it for the next launch on this handle (launches are stream-ordered)
   if (lane == 0) {
+    if (io.warp_cycles != nullptr) {
+      io.warp_cycles[(size_t)blockIdx.x * WARPS_PER_BLOCK + warp] = (unsigned long long)(clock64() - t_begin);
+    }
     __threadfence();
     const unsigned long long total = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
     if (atomicAdd(io.queue + 1, 1ull) == total - 1) {

@@ -9,6 +9,7 @@
 #pragma once
 #include <charconv>
 #include <cstddef>
+#include <optional>
 #include <cstdint>
 #include <cstdio>
 #include <stdexcept>
@@ -43,6 +44,19 @@ enum class StepSizeSelectionResult : int {
 
 // mini_opt/structs.hpp:159-164
 enum class OptimizerState : int { NOMINAL = 0, ATTEMPTING_RESTORE_LM = 1 };
+
+// mini_opt/structs.hpp:147-155.  The equality-only problem of Optimization always takes the null-space QP
+// (nonlinear.cc:83-89); NOT_POSITIVE_DEFINITE ends the solve before the iteration is logged (nonlinear.cc:103-105),
+// so every logged iteration carries SUCCESS.
+enum class QPNullSpaceTerminationState : int { SUCCESS = 0, NOT_POSITIVE_DEFINITE };
+
+// mini_opt/structs.hpp:262-274: only filled when Params::log_qp_eigenvalues is set, which Optimization never does
+// (optimization.cc:73-79); kept so that code reading NLSIteration::qp_eigenvalues compiles.
+struct QPEigenvalues {
+  double min;
+  double max;
+  double abs_min;
+};
 
 // Names as printed by the reference's ostream operators (mini_opt/source/structs.cc:17-120).
 inline const char* ToName(NLSTerminationState s) {
@@ -96,6 +110,8 @@ struct NLSIteration {
   OptimizerState optimizer_state;
   double lambda;
   Errors errors_initial;
+  QPNullSpaceTerminationState qp_outputs{QPNullSpaceTerminationState::SUCCESS};
+  std::optional<QPEigenvalues> qp_eigenvalues{};
   DirectionalDerivatives directional_derivatives;
   double penalty;
   StepSizeSelectionResult step_result;
@@ -132,6 +148,8 @@ struct NLSSolverOutputs {
   std::vector<NLSIteration> iterations;
   Errors final_errors;       // Errors at the returned variables (extra)
   double final_penalty{0};   // extra
+  // mini_opt/source/structs.cc:220-231: one QP solve per iteration on the null-space path
+  std::size_t NumQPIterations() const noexcept { return iterations.size(); }
   std::size_t NumLineSearchSteps() const noexcept {
     std::size_t n = 0;
     for (const auto& it : iterations) n += it.line_search_steps.size();

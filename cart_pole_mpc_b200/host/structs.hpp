@@ -2,6 +2,7 @@
 // optimization/structs.hpp:8-70 compile against this header unchanged (minus the Eigen conversion helpers, which the
 // GPU path does not need: states travel as four doubles).
 #pragma once
+#include <array>
 
 namespace pendulum {
 
@@ -34,6 +35,9 @@ struct SingleCartPoleState {
   SingleCartPoleState() noexcept = default;
   constexpr SingleCartPoleState(double b_x, double th_1, double b_x_dot, double th_1_dot) noexcept
       : b_x(b_x), th_1(th_1), b_x_dot(b_x_dot), th_1_dot(th_1_dot) {}
+
+  // optimization/structs.hpp:60-63 returns an Eigen::Vector4d; the same four numbers in the same order, without Eigen
+  constexpr std::array<double, 4> ToVector() const noexcept { return {b_x, th_1, b_x_dot, th_1_dot}; }
 };
 static_assert(sizeof(SingleCartPoleState) == 4 * sizeof(double), "layout must match CPMPC_STATE_STRIDE");
 

@@ -179,6 +179,10 @@ class Optimization:
         prev, has = self._impl.get_previous_solution()
         previous_solution = prev[0].tolist() if has[0] else []
         out = self._impl.step(current_state._array(), dynamics_params._array(), np.array([float(b_x_set_point)]))
+        if int(out.stats[0]["termination_state"]) < 0:
+            # the reference throws inside Solve() (nonlinear.cc:356-357; nanobind turns it into a RuntimeError); the
+            # warm start is left as it was, exactly as there (optimization.cc:84-85 is never reached)
+            raise RuntimeError("non-finite cost at the linearization point")
         log = self._impl.get_iteration_log()[0]
         predicted = [SingleCartPoleState(*row) for row in out.predicted_states[0]]
         return OptimizationOutputs(current_state, previous_solution, out.u[0].tolist(), predicted, out.stats[0], log)

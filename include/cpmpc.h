@@ -169,6 +169,26 @@ int cpmpc_closed_loop_device(cpmpc_handle h, int64_t n_steps, double* states, co
                              const double* set_points, const double* weights, double* controls_out,
                              int64_t* stats_sum, void* stream);
 
+/* Debug view INSIDE the first SQP iteration, for element-wise checks against the reference's own linearisation and
+ * QP step (CreateDynamicalConstraint, optimization/optimization.cc:99-160; QPNullSpaceSolver::Solve,
+ * dependencies/mini_opt/source/qp.cc:679-729).  Every instance builds the initial guess of Step() (warm start honoured,
+ * not modified), linearises once, solves the QP with Levenberg-Marquardt damping `lambda` (nonlinear.cc:187-189) by
+ * `qp_method` (0: what Step() would use, 1: segment-wise Riccati recursion, 2: condensed form) and stops.
+ * blocks_out: HOST [B * cpmpc_debug_stride(h)] doubles per instance:
+ *   Phi  [nseg][4][4]  d x_end / d x_start of every shooting segment (row-major; columns 0..3 of A_eq's block row)
+ *   Gam  [4][W]        d x_end / d u_k of the segment that owns knot k
+ *   e    [nseg][4]     shooting defects (b_eq of the block row)
+ *   dxs  [NS][4], du [W]   the QP step in the reference's variable order
+ *   qp_ok (1 = solved, 0 = not positive definite), f(0), c(0), lambda, 4 reserved. */
+int64_t cpmpc_debug_stride(cpmpc_handle h);
+int cpmpc_debug_first_qp(cpmpc_handle h, const double* states, const double* dyn_params, const double* set_points,
+                         const double* weights, double lambda, int qp_method, double* blocks_out);
+
+/* SM cycles (clock64) every warp of the LAST launch on this handle spent on its instances: names the straggler warp
+ * when a launch is one wave of warps and its duration is the slowest warp's (bench.py per_rank).  Synchronises the
+ * device.  Returns the number of warps; writes nothing when cycles_out is NULL or capacity is too small; -1 on error. */
+int64_t cpmpc_get_warp_cycles(cpmpc_handle h, uint64_t* cycles_out, int64_t capacity);
+
 /* Number of kernel launches issued by this library since load (for bench accounting). */
 int64_t cpmpc_launch_count(void);
 

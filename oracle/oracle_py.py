@@ -116,6 +116,16 @@ def _bind(L: C.CDLL, full: bool) -> C.CDLL:
         if not full:
             L.oracle_ref_info.restype = C.c_char_p
             L.oracle_ref_info.argtypes = []
+            # oracle/ref_glue_debug.cc: views inside the reference's solver
+            ip = C.POINTER(C.c_int)
+            L.oracle_qp_dims.restype = None
+            L.oracle_qp_dims.argtypes = [dp, ip, ip]
+            L.oracle_linearize_qp.restype = C.c_int
+            L.oracle_linearize_qp.argtypes = [dp, dp, dp, C.c_double, dp, C.c_double, dp, dp, dp, dp, dp, dp, dp]
+            L.oracle_closed_loop_trace.restype = C.c_int
+            L.oracle_closed_loop_trace.argtypes = [dp, C.c_int64, C.c_int64, dp, dp, dp, dp, dp, dp, dp, C.c_int]
+            L.oracle_solver_summary.restype = C.c_int64
+            L.oracle_solver_summary.argtypes = [C.c_int, C.c_int, dp, C.c_char_p, C.c_int64]
     if full:
         L.oracle_quadratic_approx_minimum.restype = C.c_int
         L.oracle_quadratic_approx_minimum.argtypes = [C.c_double] * 4 + [dp]
@@ -335,6 +345,79 @@ def closed_loop(opt, states, dyn, set_points, n_steps, n_threads=0):
                                        _p(term), counts.ctypes.data_as(C.POINTER(C.c_int64)),
                                        hist.ctypes.data_as(C.POINTER(C.c_int64)), int(n_threads))
     return states, controls, term, counts, hist, threads
+
+
+# ---- views inside the COMPILED REFERENCE (oracle/ref_glue_debug.cc; libref.so only) ----------------------------------
+@dataclass
+class LinearizedQP:
+    status: int           # QPNullSpaceTerminationState (0 = SUCCESS)
+    guess: np.ndarray     # [N] variables the linearisation was taken at
+    G: np.ndarray         # [N, N] (lower triangle valid)
+    c: np.ndarray         # [N]
+    A: np.ndarray         # [K, N]
+    b: np.ndarray         # [K]
+    dx: np.ndarray        # [N]
+    f: float
+    equality: float
+
+
+def _reflib():
+    with using_ref():
+        return lib()
+
+
+def qp_dims(opt):
+    n, k = C.c_int(0), C.c_int(0)
+    _reflib().oracle_qp_dims(_p(_f64(opt)), C.byref(n), C.byref(k))
+    return n.value, k.value
+
+
+def linearize_qp(opt, state, dyn, set_point=0.0, prev=None, lam=0.0) -> LinearizedQP:
+    """The reference's own QP (LinearizeAndFillQP on BuildProblem's problem) at the initial guess of Step(), and the
+    step of its QPNullSpaceSolver.  Compiled reference only."""
+    opt, state, dyn = _f64(opt), _f64(state), _f64(dyn)
+    N, K = qp_dims(opt)
+    prev = _f64(prev) if prev is not None else None
+    guess, G, c = np.zeros(N), np.zeros((N, N)), np.zeros(N)
+    A, b, dx, err = np.zeros((K, N)), np.zeros(K), np.zeros(N), np.zeros(2)
+    rc = _reflib().oracle_linearize_qp(_p(opt), _p(state), _p(dyn), float(set_point), _p(prev), float(lam), _p(guess),
+                                        _p(G), _p(c), _p(A), _p(b), _p(dx), _p(err))
+    if rc < 0:
+        raise RuntimeError("the reference threw while linearising")
+    return LinearizedQP(rc, guess, G, c, A, b, dx, float(err[0]), float(err[1]))
+
+
+@dataclass
+class ClosedLoopTrace:
+    states: np.ndarray   # [B, T, 4] plant state handed to Step at tick t
+    prev: np.ndarray     # [B, T, N] warm start Step used at tick t (zeros at t = 0: cold start)
+    u: np.ndarray        # [B, T, W]
+    stats: np.ndarray    # [B, T, 8]
+    threads: int
+
+
+def closed_loop_trace(opt, states, dyn, set_points, n_steps, n_threads=0) -> ClosedLoopTrace:
+    """optimization_test.cc:38-61 for B plants run by the compiled reference, every tick recorded."""
+    opt, states, dyn, set_points = _f64(opt), _f64(states), _f64(dyn), _f64(set_points)
+    B, T = states.shape[0], int(n_steps)
+    W, S = int(opt[1]), int(opt[2])
+    N = (W // S + 1) * 4 + W
+    st, pv = np.zeros((B, T, 4)), np.zeros((B, T, N))
+    u, stats = np.zeros((B, T, W)), np.zeros((B, T, STATS_STRIDE))
+    threads = _reflib().oracle_closed_loop_trace(_p(opt), B, T, _p(states), _p(dyn), _p(set_points), _p(st), _p(pv),
+                                                  _p(u), _p(stats), int(n_threads))
+    return ClosedLoopTrace(st, pv, u, stats, threads)
+
+
+def solver_summary(termination_state: int, iter_log) -> str:
+    """mini_opt::NLSSolverOutputs::ToString (structs.cc:256-266) of the compiled reference on a log given as the
+    [n_iterations, 27] array layout of the iteration logs."""
+    log = _f64(iter_log).reshape(-1, ITERLOG_STRIDE)
+    n = log.shape[0]
+    need = _reflib().oracle_solver_summary(int(termination_state), n, _p(log), None, 0)
+    buf = C.create_string_buffer(int(need) + 1)
+    _reflib().oracle_solver_summary(int(termination_state), n, _p(log), buf, int(need) + 1)
+    return buf.value.decode()
 
 
 class Optimization:

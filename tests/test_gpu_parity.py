@@ -6,6 +6,7 @@ agrees with ITSELF on only ~98% of config-2 instances at 1e-8), s
 bar: >= 95% of instances within 1e-8 relative final cost, plus iteration-count and termination match rates.
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -527,3 +528,241 @@ def test_cpp_facade_runs_the_reference_closed_loop_test(tmp_path):
     dyn = pp.SingleCartPoleParams(1.0, 0.1, 0.25, 9.81, 0.03, 0.1, 0.13, 0.8, 100.0)
     out = pp.Optimization(op).step(pp.SingleCartPoleState(0.0, -math.pi / 2, 0.0, 0.0), dyn, 0.0)
     assert out.solver_summary() == cpp_summary
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# round 2: solve-by-solve and element-wise comparisons with the COMPILED REFERENCE (oracle/ref_glue_debug.cc)
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("over,min_frac", [(dict(), 0.98), (dict(state_spacing=5, max_iterations=10), 0.98)])
+def test_teacher_forced_closed_loop_against_compiled_reference(oracle, over, min_frac):
+    """Config 3, teacher-forced: the compiled reference runs optimization_test.cc:38-61 for 256 plants x 100 ticks and
+    records what every Step was given; the GPU re-solves each of the 25600 ticks from the reference's plant state and
+    warm start (cpmpc_set_previous_solution + cpmpc_step) and is compared solve by solve.  Free-running trajectories
+    (test_closed_loop_matches_compiled_reference) mix solver disagreement with the chaotic divergence of an unstable
+    plant; this does not.  Two CPU implementations agree on 99.8 % here (tests/parity_floor.py); measured on B200:
+    99.5 % (defaults), 99.1 % (S=5)."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/libref.so not present")
+    from cart_pole_mpc_b200 import synthetic
+    P, T = 256, 100
+    st, dy, sp = synthetic.swingup_batch(P, seed=synthetic.SEED_CONFIG2 + 1)
+    tr = oracle.closed_loop_trace(oracle.opt_array(**over), st, dy, sp, T)
+    B = P * T
+    s = _solver(B, **over)
+    s.set_previous_solution(tr.prev.reshape(B, -1), mask=np.tile((np.arange(T) > 0).astype(np.uint8), P))
+    out = s.step(tr.states.reshape(B, 4), np.repeat(dy, T, axis=0), np.repeat(sp, T))
+    ref_stats = tr.stats.reshape(B, -1)
+    ok = _rel_cost(out, ref_stats) <= REL_COST_TOL
+    assert ok.mean() >= min_frac, ok.mean()
+    assert ok.reshape(P, T)[:, 1:].mean() >= min_frac, "warm-started ticks"
+    assert (out.stats["n_iterations"] == ref_stats[:, 1].astype(int)).mean() >= 0.995
+    assert (out.stats["termination_state"] == ref_stats[:, 0].astype(int)).mean() >= 0.995
+    ru = tr.u.reshape(B, -1)
+    du = np.abs(out.u - ru).max(axis=1) / np.maximum(np.abs(ru).max(axis=1), 1.0)
+    assert np.median(du[ok]) < 1e-10
+    # the control that is actually applied to the plant
+    assert (np.abs(out.u[:, 0] - ru[:, 0]) <= 1e-6 * np.maximum(np.abs(ru[:, 0]), 1.0)).mean() >= 0.99
+    assert ref_stats[:, 1].min() < ref_stats[:, 1].max()  # early exits and full-length solves both occur
+
+
+def _check_blocks(oracle, s, st, dy, sp, w, opt, lam, method, tol_dx):
+    W, S = int(opt[1]), int(opt[2])
+    nseg, NS = W // S, W // S + 1
+    g = s.debug_first_qp(st, dy, sp, weights=w, lam=lam, qp_method=method)
+    checked = 0
+    for i in range(st.shape[0]):
+        o_i = opt.copy()
+        if w is not None:
+            o_i[8:14] = w[i]
+        q = oracle.linearize_qp(o_i, st[i], dy[i], sp[i], lam=lam)
+        if q.status != 0:
+            continue
+        assert g["qp_ok"][i]
+        checked += 1
+        assert np.isclose(g["f0"][i], q.f, rtol=1e-13) and np.isclose(g["eq0"][i], q.equality, rtol=1e-12)
+        for k in range(nseg):
+            rows = q.A[4 * k:4 * k + 4]
+            phi, gam = rows[:, 4 * k:4 * k + 4], rows[:, 4 * NS + k * S:4 * NS + (k + 1) * S]
+            assert np.abs(g["Phi"][i, k] - phi).max() <= 1e-12 * max(1.0, np.abs(phi).max())
+            assert np.abs(g["Gam"][i][:, k * S:(k + 1) * S] - gam).max() <= 1e-12 * max(1.0, np.abs(gam).max())
+            assert np.abs(g["e"][i, k] - q.b[4 * k:4 * k + 4]).max() <= 1e-12
+        dx = np.concatenate([g["dxs"][i].ravel(), g["du"][i]])
+        assert np.abs(dx - q.dx).max() <= tol_dx * max(1.0, np.abs(q.dx).max()), (i, method, lam)
+    assert checked >= st.shape[0] - 1
+
+
+def test_first_qp_blocks_match_compiled_reference(oracle):
+    """a3 and a6 element-wise: Phi / Gamma / e of the first linearisation against the block rows of the reference's
+    A_eq / b_eq (CreateDynamicalConstraint, optimization.cc:99-160) at 1e-12, and the QP step of both device methods
+    (condensed form, segment-wise Riccati recursion; undamped and Levenberg-Marquardt damped) against
+    QPNullSpaceSolver::Solve (qp.cc:679-729) on the reference's own QP at 1e-10.  Measured on B200: Phi/Gamma 2e-14,
+    dx 2e-13 .. 1e-12 (W=40), 6e-14 (W=160)."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/libref.so not present")
+    from cart_pole_mpc_b200 import synthetic
+    st, dy, sp = synthetic.swingup_batch(32, seed=31)
+    for over in (dict(), dict(state_spacing=5, max_iterations=10)):
+        opt = oracle.opt_array(**over)
+        s = _solver(32, **over)
+        for lam, method in ((0.0, 1), (0.0, 2), (1e-2, 1), (0.5, 1)):
+            _check_blocks(oracle, s, st, dy, sp, None, opt, lam, method, 1e-10)
+        # the debug view leaves the warm start alone, and a later Step() is the ordinary cold solve
+        _, has = s.get_previous_solution()
+        assert not has.any()
+    st, dy, sp, w = synthetic.sweep_batch(12)
+    opt = oracle.opt_array(window_length=160)
+    s = _solver(12, window_length=160)
+    for lam in (0.0, 1e-2):
+        _check_blocks(oracle, s, st, dy, sp, w, opt, lam, 1, 1e-10)
+    with pytest.raises(Exception):
+        s.debug_first_qp(st, dy, sp, weights=w, qp_method=2)  # no condensed scratch on long horizons
+
+
+def test_long_horizon_512_against_compiled_reference_and_cpu_floor(oracle):
+    """Config 4 (W=160, per-instance dynamics / weights / set points), 512 cold solves.  Eight SQP iterations on a
+    1.6 s horizon amplify round-off: two CPU implementations of the reference algorithm agree with each other on
+    96.1 % of these instances at 1e-8 and the FMA-contracted CPU port on 94.9 % (tests/parity_floor.py,
+    profiles/r02_parity_floor.json); the first iteration agrees to 1e-14 on every instance and every failing instance
+    first differs in a LATER iteration (profiles/r02_b_parity_diagnose.json).  The bar is therefore the floor itself:
+    the GPU must be no worse than an FMA-contracted CPU port of the same algorithm, minus the binomial noise of 512
+    samples, and never below 90 %; iteration counts and termination states must match."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/libref.so not present")
+    import importlib.util
+    from cart_pole_mpc_b200 import synthetic
+    spec = importlib.util.spec_from_file_location("parity_floor", os.path.join(os.path.dirname(__file__), "parity_floor.py"))
+    floor = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(floor)
+    B = 512
+    over = dict(window_length=160)
+    st, dy, sp, w = synthetic.sweep_batch(B)
+    opt = oracle.opt_array(**over)
+    with oracle.using_ref():
+        ref = oracle.batch_step(opt, st, dy, sp, weights=w, want_iter_log=True)
+    fma = floor.FmaPort().batch_step(opt, st, dy, sp, weights=w, want_iter_log=False)
+    floor_frac = floor.agree(fma.stats, ref.stats)["within_1e-8"]
+    s = _solver(B, **over)
+    s.enable_iteration_log(True)
+    out = s.step(st, dy, sp, weights=w)
+    log = s.get_iteration_log()
+    rel = _rel_cost(out, ref.stats)
+    frac = (rel <= REL_COST_TOL).mean()
+    assert frac >= max(0.90, floor_frac - 0.03), (frac, floor_frac)
+    assert (rel <= 1e-6).mean() >= 0.95
+    assert (out.stats["n_iterations"] == ref.n_iterations).mean() >= 0.995
+    assert (out.stats["termination_state"] == ref.termination).mean() >= 0.995
+    # iteration 0 starts from identical variables: f(0), c(0), d_f, d_eq agree to round-off on EVERY instance
+    d0 = np.abs(log[:, 0, 2:6] - ref.iter_log[:, 0, 2:6]) / np.maximum(np.abs(ref.iter_log[:, 0, 2:6]), 1e-300)
+    assert d0.max() < 1e-10, d0.max()
+
+
+def test_two_live_handles_with_different_block_shapes():
+    """the dynamic shared-memory attribute belongs to the kernel instantiation, not to a handle.
+    A large handle (5 warps per block) must still launch after a batch-of-one handle of the same instantiation was
+    created."""
+    from cart_pole_mpc_b200 import synthetic
+    B = 8192
+    st, dy, sp = synthetic.swingup_batch(B, seed=2)
+    big = _solver(B)
+    first = big.step(st, dy, sp)
+    small = _solver(1)
+    one = small.step(st[:1], dy[:1], sp[:1])
+    big.reset()
+    again = big.step(st, dy, sp)      # failed with cudaErrorInvalidValue before the fix
+    assert np.array_equal(first.u, again.u)
+    assert np.array_equal(one.u[0], first.u[0])
+    small.reset()
+    assert np.array_equal(small.step(st[:1], dy[:1], sp[:1]).u, one.u)
+
+
+def test_rejected_instance_keeps_its_warm_start():
+    """the reference throws inside Solve() for a non-finite cost at the linearisation point
+    (nonlinear.cc:356-357) BEFORE previous_solution_ is assigned (optimization.cc:84-85): the rejected instance must
+    keep the warm start it had, and the Python mirror must raise like the C++ facade does."""
+    from cart_pole_mpc_b200 import pypendulum as pp, synthetic
+    B = 8
+    st, dy, sp = synthetic.swingup_batch(B, seed=4)
+    s = _solver(B)
+    s.step(st, dy, sp)
+    sol0, has0 = s.get_previous_solution()
+    bad = st.copy()
+    bad[3, 2] = np.nan
+    out = s.step(bad, dy, sp)
+    assert out.stats["termination_state"][3] == -1
+    assert (out.stats["termination_state"][np.arange(B) != 3] >= 0).all()
+    sol1, has1 = s.get_previous_solution()
+    assert has1.all() and np.array_equal(sol1[3], sol0[3]), "warm start of the rejected instance must be untouched"
+    assert not np.array_equal(sol1[2], sol0[2])
+    # a never-solved instance that is rejected stays cold
+    s2 = _solver(1)
+    s2.step(bad[3:4], dy[3:4], sp[3:4])
+    assert not s2.get_previous_solution()[1][0]
+    opt = pp.Optimization(pp.OptimizationParams())
+    dyn = pp.SingleCartPoleParams(*dy[0])
+    with pytest.raises(RuntimeError):
+        opt.step(pp.SingleCartPoleState(0.0, -1.5, float("nan"), 0.0), dyn, 0.0)
+    ok = opt.step(pp.SingleCartPoleState(0.0, -1.5, 0.0, 0.0), dyn, 0.0)   # and the controller is still usable, cold
+    assert ok.previous_solution == []
+
+
+def test_native_pypendulum_runs_scratch_py(oracle):
+    """The pybind11 module `pypendulum` (host/pypendulum_ext.cc: the binding list of wrapper/wrapper.cc:40-102 over the
+    C++ facade) driven by model/scratch.py:14-40's call sequence, and by the closed loop of optimization_test.cc with
+    Simulator; its solver_summary() must be byte-equal to the reference's own ToString of the same log, and equal to
+    the Python mirror's."""
+    import sys
+    from cart_pole_mpc_b200 import build, pypendulum as mirror
+    build.build_pypendulum()
+    sys.path.insert(0, build.NATIVE_DIR)
+    try:
+        import pypendulum as pp
+    finally:
+        sys.path.pop(0)
+    # model/scratch.py:22-38
+    params = pp.SingleCartPoleParams(1.0, 0.1, 0.25, 9.81, 0.05, 0.1, 0.02, 0.8, 100.0)
+    x0 = pp.SingleCartPoleState(0.0, 0.0, 0.0, 0.0)
+    op = pp.OptimizationParams()
+    op.max_iterations = 30
+    op.state_spacing = 10
+    op.window_length = 40
+    op.absolute_first_derivative_tol = 1.0e-3
+    op.u_guess_sinusoid_amplitude = 10.0
+    op.u_cost_weight = 0.0
+    op.b_x_final_cost_weight = 5.0
+    op.th_final_cost_weight = -1.0
+    op.b_x_dot_final_cost_weight = 100.0
+    op.th_dot_final_cost_weight = 100.0
+    opt = pp.Optimization(op)
+    outputs = opt.step(x0, params, 0.0)
+    text = outputs.solver_summary()
+    assert text.startswith("Iteration # 0, state = NOMINAL, lambda = 0\n") and "  termination = " in text
+    assert len(outputs.u) == 40 and len(outputs.predicted_states) == 40
+    assert all(math.isfinite(s.th_1) and math.isfinite(s.b_x_dot) for s in outputs.predicted_states)
+    # the same call sequence through the Python mirror: same kernel, same log, same text
+    mo = mirror.OptimizationParams()
+    for k in ("max_iterations", "state_spacing", "window_length", "absolute_first_derivative_tol",
+              "u_guess_sinusoid_amplitude", "u_cost_weight", "b_x_final_cost_weight", "th_final_cost_weight",
+              "b_x_dot_final_cost_weight", "th_dot_final_cost_weight"):
+        setattr(mo, k, getattr(op, k))
+    m_out = mirror.Optimization(mo).step(mirror.SingleCartPoleState(0.0, 0.0, 0.0, 0.0),
+                                         mirror.SingleCartPoleParams(1.0, 0.1, 0.25, 9.81, 0.05, 0.1, 0.02, 0.8, 100.0), 0.0)
+    assert m_out.solver_summary() == text
+    assert list(outputs.u) == list(m_out.u)
+    if oracle.ref_available():
+        n = int(m_out.stats["n_iterations"])
+        assert oracle.solver_summary(int(m_out.stats["termination_state"]), m_out._iter_log[:n]) == text
+    # Simulator + Optimization closed loop (optimization_test.cc:24-61), 30 ticks
+    sim = pp.Simulator()
+    op2 = pp.OptimizationParams()
+    op2.state_spacing, op2.max_iterations = 5, 10
+    dyn = pp.SingleCartPoleParams(1.0, 0.1, 0.25, 9.81, 0.03, 0.1, 0.13, 0.8, 100.0)
+    ctl = pp.Optimization(op2)
+    g = load_golden("closed_loop_test200.npz")
+    for t in range(30):
+        o = ctl.step(sim.get_state(), dyn, 0.0)
+        assert abs(o.u[0] - g["controls"][0][t]) <= 1e-5 * max(1.0, abs(g["controls"][0][t]))
+        sim.step(dyn, op2.control_dt, o.u[0], pp.Vector2(0, 0), pp.Vector2(0, 0))
+    with pytest.raises(Exception):
+        bad = pp.OptimizationParams()
+        bad.state_spacing = 7
+        pp.Optimization(bad)
