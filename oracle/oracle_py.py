@@ -126,6 +126,10 @@ def _bind(L: C.CDLL, full: bool) -> C.CDLL:
             L.oracle_closed_loop_trace.argtypes = [dp, C.c_int64, C.c_int64, dp, dp, dp, dp, dp, dp, dp, C.c_int]
             L.oracle_solver_summary.restype = C.c_int64
             L.oracle_solver_summary.argtypes = [C.c_int, C.c_int, dp, C.c_char_p, C.c_int64]
+            # oracle/ref_glue_double.cc: the nx = 6 problem solved by the reference's own solver and integrator
+            L.oracle_dp_ref_batch_step.restype = C.c_int
+            L.oracle_dp_ref_batch_step.argtypes = [dp, C.c_int64, dp, dp, dp, dp, dp, C.POINTER(C.c_uint8), dp, dp, dp,
+                                                   dp, dp, C.c_int]
     if full:
         L.oracle_quadratic_approx_minimum.restype = C.c_int
         L.oracle_quadratic_approx_minimum.argtypes = [C.c_double] * 4 + [dp]
@@ -328,6 +332,30 @@ def dp_batch_step(opt, states, dyn, set_points, weights=None, prev=None, has_pre
         hp = has_prev.ctypes.data_as(C.POINTER(C.c_uint8))
     threads = lib().oracle_dp_batch_step(_p(opt), B, _p(states), _p(dyn), _p(set_points), _p(weights), _p(prev), hp,
                                          _p(u), _p(pred), _p(sol), _p(stats), _p(ilog), int(n_threads))
+    return BatchResult(u, pred, sol, stats, ilog, threads)
+
+
+def dp_ref_batch_step(opt, states, dyn, set_points, weights=None, prev=None, has_prev=None, n_threads=0,
+                      want_iter_log=True) -> BatchResult:
+    """The double-pendulum controller with the COMPILED REFERENCE's solver (mini_opt SQP + null-space QP + Residual
+    scatter) and integrator templates (runge_kutta_4th_order<6>), oracle/ref_glue_double.cc.  Same contract as
+    dp_batch_step."""
+    opt = _f64(opt)
+    states, dyn, set_points = _f64(states), _f64(dyn), _f64(set_points)
+    B = states.shape[0]
+    W, S, max_it = int(opt[1]), int(opt[2]), int(opt[3])
+    N = (W // S + 1) * DP_NX + W
+    u, pred, sol = np.zeros((B, W)), np.zeros((B, W, DP_NX)), np.zeros((B, N))
+    stats = np.zeros((B, STATS_STRIDE))
+    ilog = np.zeros((B, max_it, ITERLOG_STRIDE)) if want_iter_log else None
+    weights = _f64(weights) if weights is not None else None
+    prev = _f64(prev) if prev is not None else None
+    hp = None
+    if has_prev is not None:
+        has_prev = np.ascontiguousarray(np.asarray(has_prev, dtype=np.uint8))
+        hp = has_prev.ctypes.data_as(C.POINTER(C.c_uint8))
+    threads = _reflib().oracle_dp_ref_batch_step(_p(opt), B, _p(states), _p(dyn), _p(set_points), _p(weights), _p(prev),
+                                                 hp, _p(u), _p(pred), _p(sol), _p(stats), _p(ilog), int(n_threads))
     return BatchResult(u, pred, sol, stats, ilog, threads)
 
 

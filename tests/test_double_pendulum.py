@@ -268,3 +268,55 @@ def test_double_pendulum_invalid_arguments():
     s = PlantBatchedOptimization("double", 4)
     with pytest.raises(ValueError):
         s.step(np.zeros((4, 4)), np.zeros((4, 6)), np.zeros(4))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Pinned to REFERENCE code where the reference has any: oracle/ref_glue_double.cc solves the same
+# nx = 6 problem with the compiled reference's solver (mini_opt SQP, null-space QP, Residual scatter) and integrator
+# templates (runge_kutta_4th_order<6>, mod_pi).  Only the equations of motion stay unpinned (the reference ships none).
+# ---------------------------------------------------------------------------------------------------------------------
+def test_reference_solver_arm_agrees_with_the_restatement(oracle):
+    """CPU: the nx = 6 restatement (oracle/double_cartpole.cc on oracle/sqp.cc) against the same problem driven through
+    the reference's own mini_opt + integration.hpp.  Cold and warm-started, default and mixed terminal weights."""
+    if oracle.build_ref() is None or not oracle.ref_available():
+        pytest.skip("oracle/_ref/libref.so cannot be built here")
+    from cart_pole_mpc_b200 import synthetic
+    B = 96
+    st, dy, sp = synthetic.double_swingup_batch(B, seed=13)
+    for over in (dict(), dict(state_spacing=5, max_iterations=10),
+                 dict(b_x_final_cost_weight=50.0, th_2_final_cost_weight=30.0, th_2_dot_final_cost_weight=20.0)):
+        opt = oracle.dp_opt_array(**over)
+        port = oracle.dp_batch_step(opt, st, dy, sp)
+        ref = oracle.dp_ref_batch_step(opt, st, dy, sp)
+        # first iteration from identical variables: f(0), c(0), d_f, d_eq to round-off
+        assert np.allclose(port.iter_log[:, 0, 2:6], ref.iter_log[:, 0, 2:6], rtol=1e-9, atol=1e-9)
+        assert (port.n_iterations == ref.n_iterations).mean() >= 0.97  # a chaotic instance may exit an iteration apart
+        rel = np.abs(port.merit - ref.merit) / np.maximum(np.abs(ref.merit), 1e-300)
+        assert (rel <= REL_COST_TOL).mean() >= 0.95
+        warm_p = oracle.dp_batch_step(opt, st, dy, sp, prev=ref.solution, has_prev=np.ones(B, np.uint8), want_iter_log=False)
+        warm_r = oracle.dp_ref_batch_step(opt, st, dy, sp, prev=ref.solution, has_prev=np.ones(B, np.uint8),
+                                          want_iter_log=False)
+        rel = np.abs(warm_p.merit - warm_r.merit) / np.maximum(np.abs(warm_r.merit), 1e-300)
+        assert (rel <= REL_COST_TOL).mean() >= 0.93
+        assert (warm_p.n_iterations == warm_r.n_iterations).mean() >= 0.97
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("over,min_frac", [(dict(), 0.95), (dict(state_spacing=5, max_iterations=10), 0.95)])
+def test_double_pendulum_against_reference_solver(oracle, over, min_frac):
+    """Config 5 against the compiled reference's solver + integrator on the nx = 6 problem, 2048 instances, cold; and the
+    warm-started second step from the reference arm's solution."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/libref.so not present")
+    from cart_pole_mpc_b200 import PlantBatchedOptimization, synthetic
+    B = 2048
+    st, dy, sp = synthetic.double_swingup_batch(B)
+    ref = oracle.dp_ref_batch_step(oracle.dp_opt_array(**over), st, dy, sp, want_iter_log=False)
+    s = PlantBatchedOptimization("double", B, **over)
+    out = s.step(st, dy, sp)
+    _check(out, ref, min_frac=min_frac, min_iter=0.98)
+    s.set_previous_solution(ref.solution)
+    out2 = s.step(st, dy, sp)
+    ref2 = oracle.dp_ref_batch_step(oracle.dp_opt_array(**over), st, dy, sp, prev=ref.solution,
+                                    has_prev=np.ones(B, np.uint8), want_iter_log=False)
+    _check(out2, ref2, min_frac=0.93, min_iter=0.97)
