@@ -176,13 +176,18 @@ class BatchedOptimization:
         _capi.check(self._lib.cpmpc_get_previous_solution(self._h, sol.ctypes.data, has.ctypes.data))
         return sol, has.astype(bool)
 
-    def warp_cycles(self) -> np.ndarray:
-        """SM cycles every warp of the last launch spent on its instances (cpmpc_get_warp_cycles)."""
+    PHASE_NAMES = ("setup+initial guess", "linearise", "condensed qp", "riccati qp", "derivatives+penalty",
+                   "line search", "update+exit tests", "outputs")
+
+    def warp_cycles(self, with_instances: bool = False) -> np.ndarray:
+        """SM cycles every warp of the last launch spent on its instances (cpmpc_get_warp_cycles); with
+        `with_instances` the full [n, 10] records: cycles, first instance of the warp's last batch, then the cycles per
+        solver phase (PHASE_NAMES)."""
         n = int(self._lib.cpmpc_get_warp_cycles(self._h, None, 0))
-        out = np.zeros(max(n, 0), dtype=np.uint64)
+        out = np.zeros((max(n, 0), 10), dtype=np.uint64)
         if n > 0 and self._lib.cpmpc_get_warp_cycles(self._h, out.ctypes.data, n) != n:
             raise _capi.CpmpcError("cpmpc_get_warp_cycles failed")
-        return out
+        return out if with_instances else np.ascontiguousarray(out[:, 0])
 
     # ---- debug view inside the first SQP iteration ----------------------------------------------------------------
     def debug_first_qp(self, states, dyn_params, set_points, weights=None, lam: float = 0.0, qp_method: int = 0):

@@ -128,17 +128,15 @@ void BuildLayout(KernelCfg& k) {
   k.off_xc = k.off_gam;
   k.off_uc = k.off_xc + 4 * NS;
   k.off_xkc = k.off_uc + W;
-  // Riccati stage matrix over (S controls | xi | rho), packed lower triangle
-  const int D = S + NCOL_MAX;
-  const int n_ric = D * (D + 1) / 2;
-  const int n_cond = k.condensed ? 6 * W : 0;  // condensed QP scratch: Z [4][W], tl [W], tinv [W]
+  // QP scratch: the condensed form's Z [4][W], tl [W], tinv [W]; the Riccati recursion only stages the feedback rows
+  // of ONE segment here for its forward sweep (its value function lives in registers)
+  const int n_ric = S * GAIN_STRIDE;
+  const int n_cond = k.condensed ? 6 * W : 0;
   k.off_aug = take(n_ric > n_cond ? n_ric : n_cond);
-  k.off_vbuf = take(25 + XI_DIM * NR_MAX);
-  k.off_invd = take(S);
   k.off_dyn = take(12);
   // odd stride (in doubles) so that the same field of neighbouring instances falls into different banks
   k.stride = off | 1;
-  k.kk_stride = nseg * NCOL_MAX * S;
+  k.kk_stride = W * GAIN_STRIDE;
 }
 
 int Launch(cpmpc_solver* h, KernelIO io, cudaStream_t stream) {
@@ -351,7 +349,11 @@ int cpmpc_create_ex(const cpmpc_params* params, int64_t batch, int device, uint3
   // halves its dependent chain.  Overridable for experiments.
   int base_lanes = Pow2Ceil(k.nseg);
   if (base_lanes > 32) base_lanes = 32;
-  int lanes = base_lanes;
+  // At most 8 lanes per instance in the throughput mapping: the serial phases of a solve (knot-level Riccati recursion,
+  // initial-guess and predicted-state rollouts) run on one lane per instance, so wider groups leave more of every warp
+  // idle there (W = 160: 16 lanes 1.16 M solves/s, 8 lanes 1.26 M, 4 lanes 0.84 M on one B200,
+  // profiles/r02_j_config4_lanes.txt); a lane then carries several shooting segments one after the other.
+  int lanes = base_lanes < 8 ? base_lanes : 8;
   // CPMPC_FLAG_LOW_LATENCY: two lanes per segment.  It shortens one solve's dependent chain (batch-1 latency
   // 0.73 -> 0.60 ms at the defaults) but leaves half of every warp idle during the merit rollouts: 3.88 M solves/s
   // instead of 4.28 M at B = 4096, 3.6 M instead of 5.3 M at B = 65536 (profiles/r01_lane_sweep.jsonl).  It is
@@ -445,8 +447,8 @@ int cpmpc_create_ex(const cpmpc_params* params, int64_t batch, int device, uint3
   CUDA_TRY(cudaMemset(h->d_has_prev, 0, batch));
   CUDA_TRY(cudaMemset(h->d_prev, 0, sizeof(double) * batch * k.N));
   CUDA_TRY(cudaMalloc(&h->d_kk, sizeof(double) * n_groups * k.kk_stride));
-  CUDA_TRY(cudaMalloc(&h->d_warp_cycles, sizeof(unsigned long long) * h->grid * wpb));
-  CUDA_TRY(cudaMemset(h->d_warp_cycles, 0, sizeof(unsigned long long) * h->grid * wpb));
+  CUDA_TRY(cudaMalloc(&h->d_warp_cycles, sizeof(unsigned long long) * WARP_REC * h->grid * wpb));
+  CUDA_TRY(cudaMemset(h->d_warp_cycles, 0, sizeof(unsigned long long) * WARP_REC * h->grid * wpb));
   CUDA_TRY(cudaMalloc(&h->d_queue, sizeof(unsigned long long) * 2));
   CUDA_TRY(cudaMemset(h->d_queue, 0, sizeof(unsigned long long) * 2));
   CUDA_TRY(cudaMalloc(&h->d_u_guess, sizeof(double) * k.W));
@@ -756,7 +758,7 @@ int64_t cpmpc_get_warp_cycles(cpmpc_handle h, uint64_t* cycles_out, int64_t capa
   const int64_t n = static_cast<int64_t>(h->grid) * h->warps_per_block;
   if (cycles_out == nullptr || capacity < n) return n;
   if (cudaSetDevice(h->device) != cudaSuccess) return -1;
-  if (cudaMemcpy(cycles_out, h->d_warp_cycles, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost) != cudaSuccess) {
+  if (cudaMemcpy(cycles_out, h->d_warp_cycles, sizeof(uint64_t) * WARP_REC * n, cudaMemcpyDeviceToHost) != cudaSuccess) {
     Fail(CPMPC_ERR_CUDA, "cudaMemcpy of the warp cycle counters failed");
     return -1;
   }

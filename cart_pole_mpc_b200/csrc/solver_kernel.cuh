@@ -28,10 +28,19 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/cpmpc.h"
 #include "dynamics.cuh"
 
 namespace cpmpc {
+
+// Per-warp phase profile written next to the warp cycle counters (cpmpc_get_warp_cycles): SM cycles attributed to
+//   0 instance set-up + initial guess rollout   1 linearisation   2 condensed QP   3 Riccati recursion
+//   4 directional derivatives + penalty         5 line search (merit rollouts)   6 update / exit tests
+//   7 outputs (warm start, predicted-state rollout, statistics, plant step)
+constexpr int N_PHASES = 8;
+constexpr int WARP_REC = 2 + N_PHASES;  // cycles, first instance of the last batch, then the phases
 
 constexpr int NR_MAX = 5;              // rho coordinates: affine + up to 4 hard terminal rows
 constexpr int XI_DIM = 5;              // stage state: node step (4) + previous control (1)
@@ -43,10 +52,10 @@ struct KernelCfg {
   int cps;     // chunks per shooting segment in the linearisation
   int nchunk;  // nseg * cps
   int stride;  // doubles of shared memory per instance
-  int off_xs, off_u, off_dxs, off_du, off_phi, off_e, off_gam, off_xk, off_phic, off_aug, off_vbuf, off_invd;
+  int off_xs, off_u, off_dxs, off_du, off_phi, off_e, off_gam, off_xk, off_phic, off_aug;
   int off_dyn;  // this instance's DynConst (12 doubles): phase functions reload it instead of pinning registers
   int off_xc, off_uc, off_xkc;  // line-search candidates: alias the Gamma block (dead after the QP)
-  int kk_stride;                // doubles of global scratch per group: nseg * NCOL_MAX * S Riccati gains
+  int kk_stride;                // doubles of global scratch per group: W * GAIN_STRIDE Riccati feedback rows
   double dt, rel_tol, first_tol, abs_tol, pen_init, pen_scale, rho, armijo_c1;
   double lam_fail_init, lam_dec_success, lam_dec_restore, lam_max, lam_min;
   double w_u, w_r, wt[4];
@@ -80,8 +89,10 @@ struct KernelIO {
   long long dbg_stride;
   double dbg_lambda;
   int dbg_qp;                // 0: the handle's choice, 1: Riccati recursion, 2: condensed form
-  // [grid warps] SM cycles every warp spent between its first and its last instance (clock64), or nullptr: names
-  // the straggler warp of a launch (bench.py per_rank)
+  // [grid warps][WARP_REC] SM cycles every warp spent between its first and its last instance (clock64), the first
+  // instance of the last batch it drew from the queue, and the cycles per solver phase; or nullptr.  Names the straggler
+  // warp of a launch and, when a launch is one wave, the instances it carried and where its time went
+  // (bench.py per_rank, profiles/shard_times.py)
   unsigned long long* warp_cycles;
 };
 
@@ -245,46 +256,33 @@ __device__ __forceinline__ void evaluate_errors(const Ctx& c, const Weights& w, 
   eq_out = group_sum<L>(eq, c.gmask);
 }
 
-// Column-major packed lower-triangular index of a D x D matrix: column c holds rows c..D-1 contiguously.
-__device__ __forceinline__ int cbase(const int D, const int col) { return col * D - ((col * (col - 1)) >> 1) - col; }
-// aug[cbase(D, col) + r] is entry (r, col), r >= col.
-
-// y[0..n) -= a * x[0..n) on shared memory.  Loads are issued in batches ahead of the stores so that the LDS latency
-// is paid once per batch (x and y never overlap, which the compiler cannot know).
-__device__ __forceinline__ void axpy_neg(double* y, const double* x, const double a, const int n) {
-  int r = 0;
-  for (; r + 4 <= n; r += 4) {
-    const double x0 = x[r], x1 = x[r + 1], x2 = x[r + 2], x3 = x[r + 3];
-    const double y0 = y[r], y1 = y[r + 1], y2 = y[r + 2], y3 = y[r + 3];
-    y[r] = fma(-a, x0, y0);
-    y[r + 1] = fma(-a, x1, y1);
-    y[r + 2] = fma(-a, x2, y2);
-    y[r + 3] = fma(-a, x3, y3);
-  }
-  if (r + 2 <= n) {
-    const double x0 = x[r], x1 = x[r + 1];
-    const double y0 = y[r], y1 = y[r + 1];
-    y[r] = fma(-a, x0, y0);
-    y[r + 1] = fma(-a, x1, y1);
-    r += 2;
-  }
-  if (r < n) y[r] = fma(-a, x[r], y[r]);
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
-// Equality-constrained QP of one SQP iteration (reference: QPNullSpaceSolver::Solve, qp.cc:679-729) by a segment-wise
-// Riccati recursion; see the header comment.  On entry Phi / Gam / ev hold the segment blocks, du[] the gradient of
-// the control costs.  On exit du[] and dxs[] hold the step; returns false when a pivot is not positive (the reduced
-// Hessian is not positive definite: QP_INDEFINITE).  `cdx` returns this lane's share of c_u . du.
+// Equality-constrained QP of one SQP iteration (reference: QPNullSpaceSolver::Solve, qp.cc:679-729) by a KNOT-level
+// Riccati recursion in end-of-segment coordinates: one SCALAR control per elimination step.
 //
-// Stage matrix (column-major packed lower triangle, D = S + 5 + nr):
-//        [ H_vv                     ]   v   : the S controls of the segment
-//    A = [ H_xv   H_xx              ]   xi  : (dx_s, previous control)
-//        [ h_v^T  h_x^T    C        ]   rho : (1, mu_1 .. mu_nh)
-// S steps of right-looking LDL^T elimination (no square roots: column j stays unscaled, its pivot reciprocal goes to
-// invd[j]) leave the next value function in the trailing (xi, rho) block and Z = L^-1 [H_vx h_v] in rows S.. of the
-// first S columns; the gains K = L^-T D^-1 Z follow by back-substitution.
+// Inside shooting segment s the recursion state is z = (y, p): y = Phi_s dx_s + e_s + sum_{j<i} Gamma_j v_j — the end
+// state of the segment as far as the controls already applied determine it — and p = the previous control (the
+// control-rate cost couples neighbours).  One knot i of the segment is then the scalar-input stage
+//     z+ = A z + b v,   A = diag(1, 1, 1, 1, 0),   b = (Gamma_i, 1),
+//     cost = 1/2 (w_u^2 + lambda) v^2 + 1/2 w_r^2 (v - p)^2 + g_i v
+// and the value function over (z | rho) — rho = the affine coordinate plus one multiplier coordinate per hard terminal
+// row — stays a (5 + nr) x (5 + nr) symmetric matrix (P 5x5, Q 5 x nr, C nr x nr: at most 55 numbers, in registers of
+// the group's first lane).  Every elimination is a scalar pivot piv = w_u^2 + lambda + w_r^2 + b^T P b; a non-positive
+// pivot is QP_INDEFINITE.  At a shooting node the value function is pulled back through y = Phi dx + e rho_0, and
+// Levenberg-Marquardt damping (lambda on every diagonal entry of G, nonlinear.cc:187-189) adds lambda to the node's own
+// diagonal.  The feedback rows (5 + nr numbers per knot) go to an L2-resident global scratch; the multipliers of the
+// hard terminal rows come from a (<= 4x4) Cholesky on the rho block, one forward sweep yields du and the node steps.
+//
+// Compared with eliminating the S controls of a segment from a dense (S + 10)^2 stage matrix in shared memory (round
+// 1): the same exact QP step (tests/prototypes/qp_riccati_proto.py: both within 1e-13 of an extended-precision KKT
+// solve), about 110 FP64 instructions per knot instead of several thousand shared-memory round trips per segment, no
+// stage matrix in shared memory at all, and no barrier inside the recursion.
+//
+// On entry Phi / Gam / ev hold the segment blocks and du[] the gradient of the control costs; on exit du[] and dxs[]
+// hold the step.  `cdx` returns c_u . du on the group's first lane (0 elsewhere).
 // ---------------------------------------------------------------------------------------------------------------------
+constexpr int GAIN_STRIDE = XI_DIM + NR_MAX;  // doubles of feedback per knot: 5 for z, up to 5 for rho
+
 template <int L>
 __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights& w, const double lambda,
                                            const double x_cur[4], const double target[4], double& cdx) {
@@ -296,11 +294,9 @@ __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights& w, const
   const double* Phi = c.sm + k.off_phi;
   const double* ev = c.sm + k.off_e;
   const double* Gam = c.sm + k.off_gam;
-  double* aug = c.sm + k.off_aug;
-  double* vb = c.sm + k.off_vbuf;  // [25] P (full, symmetric) then [5][NR_MAX] q
-  double* qb = vb + 25;
-  double* invd = c.sm + k.off_invd;
+  double* stage = c.sm + k.off_aug;  // [S][GAIN_STRIDE] feedback rows of one segment, staged for the forward sweep
   const double wu2 = w.w_u * w.w_u, wr2 = w.w_r * w.w_r;
+  cdx = 0.0;
 
   // hard terminal rows (negative weight, optimization.cc:236-267) and their rho coordinates
   int nh = 0;
@@ -315,8 +311,6 @@ __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights& w, const
     }
   }
   const int nr = 1 + nh;
-  const int n2 = XI_DIM + nr;
-  const int D = S + n2;
   double dT[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -324,267 +318,6 @@ __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights& w, const
     if (i == 1) d = mod_pi(d);
     dT[i] = d;
   }
-
-  // terminal value function V_N over (xi | rho), stored where a stage elimination leaves it: rows/cols S..D-1
-  for (int b = c.gl; b < n2; b += L) {
-    double* colp = aug + cbase(D, S + b) + S;  // entry (S + a, S + b) at colp[a]
-    for (int a = b; a < n2; ++a) {
-      double v = 0.0;
-      if (a < 4) {
-        if (a == b) {
-          const double wa = (a == 0) ? w.wt[0] : (a == 1) ? w.wt[1] : (a == 2) ? w.wt[2] : w.wt[3];
-          v = lambda + ((wa >= 0.0) ? wa * wa : 0.0);
-        }
-      } else if (a == XI_DIM && b < 4) {
-        const double wb = (b == 0) ? w.wt[0] : (b == 1) ? w.wt[1] : (b == 2) ? w.wt[2] : w.wt[3];
-        const double db = (b == 0) ? dT[0] : (b == 1) ? dT[1] : (b == 2) ? dT[2] : dT[3];
-        v = (wb >= 0.0) ? (wb * wb) * db : 0.0;
-      } else if (a > XI_DIM && b < 4) {
-        const int j = a - XI_DIM - 1;
-        const int hj = (j == 0) ? hcomp[0] : (j == 1) ? hcomp[1] : (j == 2) ? hcomp[2] : hcomp[3];
-        v = (b == hj) ? 1.0 : 0.0;
-      }
-      colp[a] = v;
-    }
-  }
-  CPMPC_GSYNC();
-
-  // trailing-block accessor: entry (S + a, S + b), a >= b
-#define CPMPC_TR(a, b) aug[cbase(D, S + (b)) + S + (a)]
-  bool ok = true;
-  for (int s = nseg - 1; s >= 0; --s) {
-    const double* Ph = Phi + 16 * s;
-    const double f0 = ev[4 * s], f1 = ev[4 * s + 1], f2 = ev[4 * s + 2], f3 = ev[4 * s + 3];
-    // (i) snapshot P (full 5x5) and q = p + (P f) e_0; fold f . p_r into the rho-rho column 0 (in place)
-    for (int t = c.gl; t < 25 + XI_DIM * nr + nh; t += L) {
-      if (t < 25) {
-        const int a = t / 5, b = t - 5 * a;
-        vb[t] = (a >= b) ? CPMPC_TR(a, b) : CPMPC_TR(b, a);
-      } else if (t < 25 + XI_DIM * nr) {
-        const int t2 = t - 25;
-        const int r = t2 / XI_DIM, a = t2 - XI_DIM * r;
-        double v = CPMPC_TR(XI_DIM + r, a);
-        if (r == 0) {
-          const double p0 = CPMPC_TR(a, 0);
-          const double p1 = (a >= 1) ? CPMPC_TR(a, 1) : CPMPC_TR(1, a);
-          const double p2 = (a >= 2) ? CPMPC_TR(a, 2) : CPMPC_TR(2, a);
-          const double p3 = (a >= 3) ? CPMPC_TR(a, 3) : CPMPC_TR(3, a);
-          v += p0 * f0 + p1 * f1 + p2 * f2 + p3 * f3;
-        }
-        qb[a * NR_MAX + r] = v;
-      } else {
-        const int r = t - 25 - XI_DIM * nr + 1;  // 1..nh
-        CPMPC_TR(XI_DIM + r, XI_DIM) += CPMPC_TR(XI_DIM + r, 0) * f0 + CPMPC_TR(XI_DIM + r, 1) * f1 +
-                                        CPMPC_TR(XI_DIM + r, 2) * f2 + CPMPC_TR(XI_DIM + r, 3) * f3;
-      }
-    }
-    CPMPC_GSYNC();
-
-    // (ii) assemble the stage matrix: every lane writes whole columns (contiguous)
-    for (int t = c.gl; t < S + XI_DIM; t += L) {
-      double* colp = aug + cbase(D, t);  // entry (r, t) at colp[r]
-      if (t < S) {
-        const int j = t, col = s * S + j;
-        const double g0 = Gam[col], g1 = Gam[W + col], g2 = Gam[2 * W + col], g3 = Gam[3 * W + col];
-        const double g4 = (j == S - 1) ? 1.0 : 0.0;
-        double PG[XI_DIM];
-#pragma unroll
-        for (int a = 0; a < XI_DIM; ++a)
-          PG[a] = vb[5 * a] * g0 + vb[5 * a + 1] * g1 + vb[5 * a + 2] * g2 + vb[5 * a + 3] * g3 + vb[5 * a + 4] * g4;
-        for (int i = j; i < S; ++i) {
-          const int ci = s * S + i;
-          double v = Gam[ci] * PG[0] + Gam[W + ci] * PG[1] + Gam[2 * W + ci] * PG[2] + Gam[3 * W + ci] * PG[3];
-          if (i == S - 1) v += PG[4];
-          if (i == j) v += wu2 + lambda + wr2 * ((col + 1 < W) ? 2.0 : 1.0);
-          if (i == j + 1) v -= wr2;
-          colp[i] = v;
-        }
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc)
-          colp[S + cc] = Ph[cc] * PG[0] + Ph[4 + cc] * PG[1] + Ph[8 + cc] * PG[2] + Ph[12 + cc] * PG[3];
-        colp[S + 4] = (j == 0 && s > 0) ? -wr2 : 0.0;
-        for (int r = 0; r < nr; ++r) {
-          double v = g0 * qb[r] + g1 * qb[NR_MAX + r] + g2 * qb[2 * NR_MAX + r] + g3 * qb[3 * NR_MAX + r] +
-                     g4 * qb[4 * NR_MAX + r];
-          if (r == 0) v += du[col];
-          colp[S + XI_DIM + r] = v;
-        }
-      } else {
-        const int cc = t - S;  // xi column
-        if (cc < 4) {
-          const double h0 = Ph[cc], h1 = Ph[4 + cc], h2 = Ph[8 + cc], h3 = Ph[12 + cc];
-          double PF[4];
-#pragma unroll
-          for (int a = 0; a < 4; ++a) PF[a] = vb[5 * a] * h0 + vb[5 * a + 1] * h1 + vb[5 * a + 2] * h2 + vb[5 * a + 3] * h3;
-          for (int c2 = cc; c2 < 4; ++c2) {
-            double v = Ph[c2] * PF[0] + Ph[4 + c2] * PF[1] + Ph[8 + c2] * PF[2] + Ph[12 + c2] * PF[3];
-            if (c2 == cc && s > 0) v += lambda;
-            colp[S + c2] = v;
-          }
-          colp[S + 4] = 0.0;
-          for (int r = 0; r < nr; ++r)
-            colp[S + XI_DIM + r] = h0 * qb[r] + h1 * qb[NR_MAX + r] + h2 * qb[2 * NR_MAX + r] + h3 * qb[3 * NR_MAX + r];
-        } else {
-          colp[S + 4] = 0.0;
-          for (int r = 0; r < nr; ++r) colp[S + XI_DIM + r] = 0.0;
-        }
-      }
-    }
-    CPMPC_GSYNC();
-
-    // Two implementations of the same elimination, bit-identical in their results (profiles/ab_compare.py).  Wide
-    // lane groups (L >= 8: long horizons, one column per lane, several warps per scheduler) are instruction-bound and
-    // keep the right-looking form; narrow groups (L <= 4: the default horizon, Levenberg-Marquardt iterations only,
-    // one warp per scheduler) are latency-bound and use the left-looking form below, 5-8 % faster end to end on
-    // LM-heavy batches.
-    if constexpr (L >= 8) {
-    // (iii) eliminate the S controls: right-looking LDL^T steps over the whole D x D matrix, one trailing column per
-    // lane.  The lane that owns column j + 1 handles it first and publishes the reciprocal of the next pivot.
-    if (c.gl == 0) {
-      const double piv = aug[0];
-      invd[0] = (piv > 0.0) ? fm::rcp(piv) : -1.0;
-    }
-    CPMPC_GSYNC();
-    for (int j = 0; j < S; ++j) {
-      const double rd = invd[j];
-      if (!(rd > 0.0)) {
-        ok = false;
-        break;
-      }
-      const double* colj = aug + cbase(D, j);  // (r, j) at colj[r]
-      for (int cc = j + 1 + c.gl; cc < D; cc += L) {
-        double* colc = aug + cbase(D, cc);
-        const double l = colj[cc] * rd;
-        if (cc == j + 1 && cc < S) {
-          // next pivot first, so that its reciprocal is ready when the others reach the barrier
-          const double piv = fma(-l, colj[cc], colc[cc]);
-          colc[cc] = piv;
-          invd[cc] = (piv > 0.0) ? fm::rcp(piv) : -1.0;
-          axpy_neg(colc + cc + 1, colj + cc + 1, l, D - cc - 1);
-        } else {
-          axpy_neg(colc + cc, colj + cc, l, D - cc);
-        }
-      }
-      CPMPC_GSYNC();
-    }
-    } else {
-    // (iii) eliminate the S controls: LEFT-looking LDL^T.  Every entry (r, c) of the factor / Schur complement is
-    //   a(r, c) - sum_{i < min(c, S)} (a(c, i) / d_i) a(r, i),   accumulated in increasing i with one FMA per term
-    // - exactly the updates, in exactly the order, that a right-looking elimination applies to that entry (so the
-    // result is bit-identical to it) - but the running value stays in a register instead of making a shared-memory
-    // round trip per elimination step, and the loads of a chain do not depend on each other.  Phase A finalises the
-    // control columns one after the other (rows split across the lanes, one barrier per column, the pivot reciprocal
-    // published with it); phase B then updates the trailing (xi, rho) block, one column per lane, without barriers.
-    {
-      constexpr int R = 4;  // rows per register chunk
-      for (int j = 0; j < S; ++j) {
-        const int cbj = cbase(D, j);
-        for (int r0 = j + R * c.gl; r0 < D; r0 += R * L) {
-          int rr[R];
-          double y[R];
-#pragma unroll
-          for (int t = 0; t < R; ++t) {
-            rr[t] = min(r0 + t, D - 1);
-            y[t] = aug[cbj + rr[t]];
-          }
-          int cb = 0;
-          for (int i = 0; i < j; ++i) {
-            const double* ci = aug + cb;  // column i: entry (r, i) at ci[r]
-            const double l = ci[j] * invd[i];
-#pragma unroll
-            for (int t = 0; t < R; ++t) y[t] = fma(-l, ci[rr[t]], y[t]);
-            cb += D - i - 1;
-          }
-#pragma unroll
-          for (int t = 0; t < R; ++t)
-            if (r0 + t < D) aug[cbj + r0 + t] = y[t];
-          if (r0 == j) invd[j] = (y[0] > 0.0) ? fm::rcp(y[0]) : -1.0;
-        }
-        CPMPC_GSYNC();
-        if (!(invd[j] > 0.0)) {
-          ok = false;
-          break;
-        }
-      }
-      if (ok) {
-        for (int cc = S + c.gl; cc < D; cc += L) {
-          const int cbc = cbase(D, cc);
-          for (int r0 = cc; r0 < D; r0 += R) {
-            int rr[R];
-            double y[R];
-#pragma unroll
-            for (int t = 0; t < R; ++t) {
-              rr[t] = min(r0 + t, D - 1);
-              y[t] = aug[cbc + rr[t]];
-            }
-            int cb = 0;
-            for (int i = 0; i < S; ++i) {
-              const double* ci = aug + cb;
-              const double l = ci[cc] * invd[i];
-#pragma unroll
-              for (int t = 0; t < R; ++t) y[t] = fma(-l, ci[rr[t]], y[t]);
-              cb += D - i - 1;
-            }
-#pragma unroll
-            for (int t = 0; t < R; ++t)
-              if (r0 + t < D) aug[cbc + r0 + t] = y[t];
-          }
-        }
-      }
-      CPMPC_GSYNC();
-    }
-    }
-    if (!ok) break;
-
-    // (iv) gains: row S + q of the panel holds Z[:, q]; x_i = rd_i (z_i - sum_{j > i} a(j, i) x_j).
-    {
-      // Left-looking form: the sum of one unknown is accumulated in a register in the order j = S-1 .. i+1 (the order
-      // in which a right-looking sweep applies the same FMAs to z_i: bit-identical to the first implementation,
-      // profiles/ab_compare.py); solved unknowns are parked in the dead z slots of their columns, the latest one stays
-      // in a register, and two right-hand sides are interleaved per lane for instruction-level parallelism.
-      for (int q0 = c.gl; q0 < n2; q0 += 2 * L) {
-        const int q1 = q0 + L;
-        const bool two = q1 < n2;
-        const int ra = S + q0, rb = two ? S + q1 : ra;
-        double* dsta = c.kk + ((size_t)s * NCOL_MAX + q0) * S;
-        double* dstb = c.kk + ((size_t)s * NCOL_MAX + (two ? q1 : q0)) * S;
-        double xa = 0.0, xb = 0.0;
-        int cbi = cbase(D, S - 1);
-        const int cb_last = cbi;
-        for (int i = S - 1; i >= 0; --i) {
-          double* ci = aug + cbi;  // column i: a(j, i) at ci[j]
-          double acca = ci[ra], accb = ci[rb];
-          int ob = cb_last;  // column j = S-1
-          for (int j = S - 1; j > i + 1; --j) {
-            const double a = ci[j];
-            acca = fma(-a, aug[ob + ra], acca);
-            accb = fma(-a, aug[ob + rb], accb);
-            ob -= (D - j);  // cbase(D, j - 1)
-          }
-          if (i < S - 1) {
-            const double a = ci[i + 1];
-            acca = fma(-a, xa, acca);
-            accb = fma(-a, xb, accb);
-          }
-          const double rd = invd[i];
-          xa = acca * rd;
-          xb = accb * rd;
-          __stcg(dsta + i, xa);
-          ci[ra] = xa;
-          if (two) {
-            __stcg(dstb + i, xb);
-            ci[rb] = xb;
-          }
-          cbi -= (D - i);  // cbase(D, i - 1)
-        }
-      }
-    }
-    CPMPC_GSYNC();
-  }
-  ok = __all_sync(c.gmask, ok);
-  if (!ok) return false;
-
-  // multipliers of the hard terminal rows: x_N[h_j](mu) + d_j = 0 with x_N[h_j] = p_j . xi_0 + C_j0 + sum_k C_jk mu_k
   double m0[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -592,106 +325,276 @@ __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights& w, const
     if (i == 1) d = mod_pi(d);
     m0[i] = -d;
   }
+
+  bool ok = true;
   double coef[NR_MAX] = {1.0, 0.0, 0.0, 0.0, 0.0};
-  if (nh > 0) {
-    double Mh[4][4], rhs[4];
+  // The recursion is instantiated for NRC = 4 rho coordinates (the default problem: three hard terminal rows) and for
+  // the general NR_MAX = 5: the Q / C updates are a third of its work and an unused column costs as much as a used one.
+  auto backward = [&](auto nrc_tag) {
+    constexpr int NRC = decltype(nrc_tag)::value;
+    // ---- backward recursion, registers of the first lane ------------------------------------------------------------
+    // P symmetric 5x5 (upper triangle used: P[i][j], i <= j), Q 5 x NRC, C symmetric (upper triangle)
+    double P[XI_DIM][XI_DIM], Q[XI_DIM][NRC], C[NRC][NRC];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      rhs[j] = 0.0;
+    for (int i = 0; i < XI_DIM; ++i) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) Mh[j][q] = (j == q) ? 1.0 : 0.0;
-      if (j < nh) {
-        const int rj = XI_DIM + 1 + j;
-        const int hj = hcomp[j];
-        const double dj = (hj == 0) ? dT[0] : (hj == 1) ? dT[1] : (hj == 2) ? dT[2] : dT[3];
-        rhs[j] = CPMPC_TR(rj, 0) * m0[0] + CPMPC_TR(rj, 1) * m0[1] + CPMPC_TR(rj, 2) * m0[2] +
-                 CPMPC_TR(rj, 3) * m0[3] + CPMPC_TR(rj, XI_DIM) + dj;
+      for (int j = 0; j < XI_DIM; ++j) P[i][j] = 0.0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (q <= j) Mh[j][q] = -CPMPC_TR(rj, XI_DIM + 1 + q);
-      }
+      for (int r = 0; r < NRC; ++r) Q[i][r] = 0.0;
     }
-    // Cholesky of the (nh x nh) lower triangle, rows >= nh are identity
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      double d = Mh[j][j];
+    for (int r = 0; r < NRC; ++r)
 #pragma unroll
-      for (int q = 0; q < j; ++q) d -= Mh[j][q] * Mh[j][q];
-      if (!(d > 0.0)) ok = false;
-      const double inv = 1.0 / sqrt(d);
-      Mh[j][j] = inv;  // keep the reciprocal
-#pragma unroll
-      for (int i = j + 1; i < 4; ++i) {
-        double sacc = Mh[i][j];
-#pragma unroll
-        for (int q = 0; q < j; ++q) sacc -= Mh[i][q] * Mh[j][q];
-        Mh[i][j] = sacc * inv;
-      }
-    }
+      for (int q = 0; q < NRC; ++q) C[r][q] = 0.0;
+    // terminal value function (optimization.cc:236-267): soft rows are costs, hard rows couple to their multiplier
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      double sacc = rhs[i];
+      const bool soft = w.wt[i] >= 0.0;
+      const double w2 = soft ? w.wt[i] * w.wt[i] : 0.0;
+      P[i][i] = lambda + w2;
+      Q[i][0] = w2 * dT[i];
 #pragma unroll
-      for (int q = 0; q < i; ++q) sacc -= Mh[i][q] * rhs[q];
-      rhs[i] = sacc * Mh[i][i];
+      for (int j = 0; j < 4; ++j)
+        if (j < nh && 1 + j < NRC && hcomp[j] == i) Q[i][1 + j] = 1.0;
     }
+    for (int s = nseg - 1; s >= 0 && ok; --s) {
+      for (int i = S - 1; i >= 0; --i) {
+        const int col = s * S + i;
+        const double b0 = Gam[col], b1 = Gam[W + col], b2 = Gam[2 * W + col], b3 = Gam[3 * W + col];
+        const double gk = du[col];
+        // P b (b4 = 1), symmetric storage
+        double Pb[XI_DIM];
 #pragma unroll
-    for (int i = 3; i >= 0; --i) {
-      double sacc = rhs[i];
+        for (int a = 0; a < XI_DIM; ++a) {
+          const double pa0 = (a <= 0) ? P[a][0] : P[0][a], pa1 = (a <= 1) ? P[a][1] : P[1][a];
+          const double pa2 = (a <= 2) ? P[a][2] : P[2][a], pa3 = (a <= 3) ? P[a][3] : P[3][a];
+          Pb[a] = fma(pa0, b0, fma(pa1, b1, fma(pa2, b2, fma(pa3, b3, P[a][4]))));
+        }
+        const double bPb = fma(Pb[0], b0, fma(Pb[1], b1, fma(Pb[2], b2, fma(Pb[3], b3, Pb[4]))));
+        const double piv = (wu2 + lambda + wr2) + bPb;
+        if (!(piv > 0.0)) {
+          ok = false;
+          break;
+        }
+        const double inv = fm::rcp(piv);
+        const double rz[XI_DIM] = {Pb[0], Pb[1], Pb[2], Pb[3], (col > 0) ? -wr2 : 0.0};
+        double rr[NRC], kz[XI_DIM], kr[NRC];
 #pragma unroll
-      for (int q = i + 1; q < 4; ++q) sacc -= Mh[q][i] * rhs[q];
-      rhs[i] = sacc * Mh[i][i];
+        for (int r = 0; r < NRC; ++r) {
+          rr[r] = fma(Q[0][r], b0, fma(Q[1][r], b1, fma(Q[2][r], b2, fma(Q[3][r], b3, Q[4][r]))));
+          if (r == 0) rr[r] += gk;
+          kr[r] = rr[r] * inv;
+        }
+#pragma unroll
+        for (int a = 0; a < XI_DIM; ++a) kz[a] = rz[a] * inv;
+        double* dst = c.kk + (size_t)col * GAIN_STRIDE;
+#pragma unroll
+        for (int a = 0; a < XI_DIM; ++a) __stcg(dst + a, kz[a]);
+#pragma unroll
+        for (int r = 0; r < NR_MAX; ++r) __stcg(dst + XI_DIM + r, (r < NRC) ? kr[r < NRC ? r : 0] : 0.0);
+        // value function after the knot: the previous-control coordinate is replaced by this knot's own
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+#pragma unroll
+          for (int bb = a; bb < 4; ++bb) P[a][bb] = fma(-rz[a], kz[bb], P[a][bb]);
+          P[a][4] = -rz[a] * kz[4];
+#pragma unroll
+          for (int r = 0; r < NRC; ++r) Q[a][r] = fma(-rz[a], kr[r], Q[a][r]);
+        }
+        P[4][4] = fma(-rz[4], kz[4], (col > 0) ? wr2 : 0.0);
+#pragma unroll
+        for (int r = 0; r < NRC; ++r) {
+          Q[4][r] = -rz[4] * kr[r];
+#pragma unroll
+          for (int q = r; q < NRC; ++q) C[r][q] = fma(-rr[r], kr[q], C[r][q]);
+        }
+      }
+      if (!ok) break;
+      // shooting node s: y = Phi dx_s + e_s rho_0; then lambda on dx_s (dx_0 is fixed by the initial-state rows)
+      const double* Ph = Phi + 16 * s;
+      const double f0 = ev[4 * s], f1 = ev[4 * s + 1], f2 = ev[4 * s + 2], f3 = ev[4 * s + 3];
+      double Pf[XI_DIM];
+#pragma unroll
+      for (int a = 0; a < XI_DIM; ++a) {
+        const double pa0 = (a <= 0) ? P[a][0] : P[0][a], pa1 = (a <= 1) ? P[a][1] : P[1][a];
+        const double pa2 = (a <= 2) ? P[a][2] : P[2][a], pa3 = (a <= 3) ? P[a][3] : P[3][a];
+        Pf[a] = pa0 * f0 + pa1 * f1 + pa2 * f2 + pa3 * f3;
+      }
+      // C picks up f . Q (row / column 0) and f . P f; only the rows of the multipliers and column 0 are read later
+      {
+        const double fq0 = Q[0][0] * f0 + Q[1][0] * f1 + Q[2][0] * f2 + Q[3][0] * f3;
+        C[0][0] += 2.0 * fq0 + (Pf[0] * f0 + Pf[1] * f1 + Pf[2] * f2 + Pf[3] * f3);
+#pragma unroll
+        for (int r = 1; r < NRC; ++r) C[0][r] += Q[0][r] * f0 + Q[1][r] * f1 + Q[2][r] * f2 + Q[3][r] * f3;
+      }
+#pragma unroll
+      for (int a = 0; a < XI_DIM; ++a) Q[a][0] += Pf[a];
+      // Q <- blockdiag(Phi, 1)^T Q
+#pragma unroll
+      for (int r = 0; r < NRC; ++r) {
+        const double q0 = Q[0][r], q1 = Q[1][r], q2 = Q[2][r], q3 = Q[3][r];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) Q[a][r] = Ph[a] * q0 + Ph[4 + a] * q1 + Ph[8 + a] * q2 + Ph[12 + a] * q3;
+      }
+      // P <- blockdiag(Phi, 1)^T P blockdiag(Phi, 1)
+      {
+        double T[4][4];  // T = P44 Phi  (P44 = the 4x4 block, symmetric)
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const double pa0 = (a <= 0) ? P[a][0] : P[0][a], pa1 = (a <= 1) ? P[a][1] : P[1][a];
+            const double pa2 = (a <= 2) ? P[a][2] : P[2][a], pa3 = (a <= 3) ? P[a][3] : P[3][a];
+            T[a][j] = pa0 * Ph[j] + pa1 * Ph[4 + j] + pa2 * Ph[8 + j] + pa3 * Ph[12 + j];
+          }
+        const double p04 = P[0][4], p14 = P[1][4], p24 = P[2][4], p34 = P[3][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+#pragma unroll
+          for (int j = a; j < 4; ++j)
+            P[a][j] = Ph[a] * T[0][j] + Ph[4 + a] * T[1][j] + Ph[8 + a] * T[2][j] + Ph[12 + a] * T[3][j];
+          P[a][4] = Ph[a] * p04 + Ph[4 + a] * p14 + Ph[8 + a] * p24 + Ph[12 + a] * p34;
+          if (s > 0) P[a][a] += lambda;
+        }
+      }
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) coef[1 + j] = (j < nh) ? rhs[j] : 0.0;
-    if (!ok) return false;
-  }
 
-  // forward sweep: v = -(K xi + k . coef), xi+ = Phi xi + Gam v + e
-  double xi[XI_DIM] = {m0[0], m0[1], m0[2], m0[3], 0.0};
+    // ---- multipliers of the hard terminal rows: stationarity in mu_j ------------------------------------------------
+    //   Q[:4][1+j] . m0 + C[0][1+j] + sum_q C[1+j][1+q] mu_q + d_j = 0   (the rho-rho block is negative definite)
+    if (ok && nh > 0) {
+      double Mh[4][4], rhs[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        rhs[j] = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) Mh[j][q] = (j == q) ? 1.0 : 0.0;
+        if (j < nh && 1 + j < NRC) {
+          const int hj = hcomp[j];
+          const double dj = (hj == 0) ? dT[0] : (hj == 1) ? dT[1] : (hj == 2) ? dT[2] : dT[3];
+          constexpr int jj_max = NRC - 1;
+          const int jj = (1 + j <= jj_max) ? 1 + j : jj_max;
+          rhs[j] = Q[0][jj] * m0[0] + Q[1][jj] * m0[1] + Q[2][jj] * m0[2] + Q[3][jj] * m0[3] + C[0][jj] + dj;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (q <= j && q < nh) Mh[j][q] = -C[(1 + q < NRC) ? 1 + q : 0][(1 + j < NRC) ? 1 + j : 0];
+        }
+      }
+      // Cholesky of the (nh x nh) lower triangle, rows >= nh are identity
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double d = Mh[j][j];
+#pragma unroll
+        for (int q = 0; q < j; ++q) d -= Mh[j][q] * Mh[j][q];
+        if (!(d > 0.0)) ok = false;
+        const double inv = 1.0 / sqrt(d);
+        Mh[j][j] = inv;  // keep the reciprocal
+#pragma unroll
+        for (int i = j + 1; i < 4; ++i) {
+          double sacc = Mh[i][j];
+#pragma unroll
+          for (int q = 0; q < j; ++q) sacc -= Mh[i][q] * Mh[j][q];
+          Mh[i][j] = sacc * inv;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        double sacc = rhs[i];
+#pragma unroll
+        for (int q = 0; q < i; ++q) sacc -= Mh[i][q] * rhs[q];
+        rhs[i] = sacc * Mh[i][i];
+      }
+#pragma unroll
+      for (int i = 3; i >= 0; --i) {
+        double sacc = rhs[i];
+#pragma unroll
+        for (int q = i + 1; q < 4; ++q) sacc -= Mh[q][i] * rhs[q];
+        rhs[i] = sacc * Mh[i][i];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) coef[1 + j] = (j < nh) ? rhs[j] : 0.0;
+    }
+  };
+  if (c.gl == 0) {
+    if (nr <= 4) {
+      backward(std::integral_constant<int, 4>{});
+    } else {
+      backward(std::integral_constant<int, NR_MAX>{});
+    }
+  }
+  ok = __all_sync(c.gmask, ok);
+  if (!ok) return false;
+
+  // ---- forward sweep: v = -(k_z . z + k_rho . coef), y += Gamma v.  The feedback rows of a segment are copied from
+  // the global scratch to shared memory by the whole group (one L2 round trip per segment instead of one per knot).
+  double y0 = m0[0], y1 = m0[1], y2 = m0[2], y3 = m0[3], pv = 0.0;
   if (c.gl == 0) {
     dxs[0] = m0[0];
     dxs[1] = m0[1];
     dxs[2] = m0[2];
     dxs[3] = m0[3];
   }
-  cdx = 0.0;
+  // rows of a segment: S * GAIN_STRIDE doubles, NPF per lane (prefetched into registers one segment ahead, so the L2
+  // round trip of segment s + 1 overlaps the first lane's work on segment s)
+  constexpr int NPF = 4;
+  const int n_rows = S * GAIN_STRIDE;
+  const bool fits = n_rows <= NPF * L;
+  double pf[NPF];
+  auto fetch = [&](const int seg) {
+    const double* src = c.kk + (size_t)seg * n_rows;
+#pragma unroll
+    for (int q = 0; q < NPF; ++q) {
+      const int t = c.gl + q * L;
+      pf[q] = (t < n_rows) ? __ldcg(src + t) : 0.0;
+    }
+  };
+  CPMPC_GSYNC();  // the backward sweep's stores are visible to the group
+  if (fits) fetch(0);
   for (int s = 0; s < nseg; ++s) {
-    const double* kks = c.kk + (size_t)s * NCOL_MAX * S;
-    for (int j = c.gl; j < S; j += L) {
-      double acc = 0.0;
+    if (fits) {
 #pragma unroll
-      for (int q = 0; q < XI_DIM; ++q) acc += __ldcg(kks + q * S + j) * xi[q];
-#pragma unroll
-      for (int r = 0; r < NR_MAX; ++r)
-        if (r < nr) acc += __ldcg(kks + (XI_DIM + r) * S + j) * coef[r];
-      const int col = s * S + j;
-      const double v = -acc;
-      cdx += du[col] * v;  // du[] still holds c_u
-      du[col] = v;
-    }
-    CPMPC_GSYNC();
-    const double* Ph = Phi + 16 * s;
-    for (int a = c.gl; a < 4; a += L) {
-      double n0 = Ph[4 * a] * xi[0] + Ph[4 * a + 1] * xi[1] + ev[4 * s + a];
-      double n1 = Ph[4 * a + 2] * xi[2] + Ph[4 * a + 3] * xi[3];
-      const double* ga = Gam + a * W + s * S;
-      const double* vv = du + s * S;
-      int j = 0;
-      for (; j + 1 < S; j += 2) {
-        n0 += ga[j] * vv[j];
-        n1 += ga[j + 1] * vv[j + 1];
+      for (int q = 0; q < NPF; ++q) {
+        const int t = c.gl + q * L;
+        if (t < n_rows) stage[t] = pf[q];
       }
-      if (j < S) n0 += ga[j] * vv[j];
-      dxs[4 * (s + 1) + a] = n0 + n1;
+      if (s + 1 < nseg) fetch(s + 1);
+    } else {
+      const double* src = c.kk + (size_t)s * n_rows;
+      for (int t = c.gl; t < n_rows; t += L) stage[t] = __ldcg(src + t);
     }
     CPMPC_GSYNC();
-#pragma unroll
-    for (int a = 0; a < 4; ++a) xi[a] = dxs[4 * (s + 1) + a];
-    xi[4] = du[s * S + S - 1];
+    if (c.gl == 0) {
+      const double* Ph = Phi + 16 * s;
+      const double n0 = Ph[0] * y0 + Ph[1] * y1 + Ph[2] * y2 + Ph[3] * y3 + ev[4 * s];
+      const double n1 = Ph[4] * y0 + Ph[5] * y1 + Ph[6] * y2 + Ph[7] * y3 + ev[4 * s + 1];
+      const double n2 = Ph[8] * y0 + Ph[9] * y1 + Ph[10] * y2 + Ph[11] * y3 + ev[4 * s + 2];
+      const double n3 = Ph[12] * y0 + Ph[13] * y1 + Ph[14] * y2 + Ph[15] * y3 + ev[4 * s + 3];
+      y0 = n0;
+      y1 = n1;
+      y2 = n2;
+      y3 = n3;
+      for (int i = 0; i < S; ++i) {
+        const int col = s * S + i;
+        const double* g = stage + i * GAIN_STRIDE;
+        double acc = g[0] * y0 + g[1] * y1 + g[2] * y2 + g[3] * y3 + g[4] * pv;
+        double acc2 = g[XI_DIM] * coef[0] + g[XI_DIM + 1] * coef[1] + g[XI_DIM + 2] * coef[2] + g[XI_DIM + 3] * coef[3] +
+                      g[XI_DIM + 4] * coef[4];
+        const double v = -(acc + acc2);
+        cdx = fma(du[col], v, cdx);  // du[] still holds c_u
+        du[col] = v;
+        y0 = fma(Gam[col], v, y0);
+        y1 = fma(Gam[W + col], v, y1);
+        y2 = fma(Gam[2 * W + col], v, y2);
+        y3 = fma(Gam[3 * W + col], v, y3);
+        pv = v;
+      }
+      dxs[4 * (s + 1)] = y0;
+      dxs[4 * (s + 1) + 1] = y1;
+      dxs[4 * (s + 1) + 2] = y2;
+      dxs[4 * (s + 1) + 3] = y3;
+    }
+    CPMPC_GSYNC();  // the rows of this segment have been consumed
   }
   return true;
-#undef CPMPC_TR
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -988,8 +891,15 @@ struct SolveResult {
 template <int L>
 __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, const Weights& w,
                                             const double x_cur[4], const double& set_point, const double& u_prev,
-                                            double* iter_log, SolveResult& res, double* dbg = nullptr,
+                                            double* iter_log, SolveResult& res, long long* ph, double* dbg = nullptr,
                                             const double dbg_lambda = 0.0, const int dbg_qp = 0) {
+  // ph[0..N_PHASES) accumulate cycles per phase, ph[N_PHASES] is the time of the last mark
+#define CPMPC_MARK(idx)                 \
+  do {                                  \
+    const long long now_ = clock64();   \
+    ph[idx] += now_ - ph[N_PHASES];     \
+    ph[N_PHASES] = now_;                \
+  } while (0)
   const KernelCfg& k = *c.cfg;
   double* xs = c.sm + k.off_xs;
   double* u = c.sm + k.off_u;
@@ -1211,6 +1121,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
         active = false;
       }
     }
+    CPMPC_MARK(1);
 
     // ---- QP step (qp.cc:679-729) ---------------------------------------------------------------------------------
     double cdx = 0.0;
@@ -1227,48 +1138,9 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
       need_riccati = !qp_ok && !(dbg != nullptr && dbg_qp == 2);
       if (need_riccati) tri_valid = false;  // the Riccati stage matrix shares the scratch of the tridiagonal factor
     }
-    if constexpr (L < 32 && L <= 4) {
-      // Narrow lane groups (short horizons) reach the Riccati recursion only for Levenberg-Marquardt iterations and as
-      // the fallback of the condensed form: a handful of instances per batch.  While one group runs it the other
-      // groups of the warp could only wait, so the WHOLE WARP works on that one instance instead (its blocks are in its
-      // own shared memory; the per-instance scalars are broadcast from its first lane): about 6 x shorter than L
-      // lanes on it alone.  This is what bounded the slowest rank of an 8-GPU run.
-      unsigned need_mask = __ballot_sync(0xffffffffu, need_riccati);
-      const int lane = (int)(threadIdx.x & 31);
-      const int g_mine = lane / L;
-      while (need_mask != 0u) {
-        const int src = __ffs(need_mask) - 1;  // first lane of the first group that needs it
-        const int g_src = src / L;
-        Weights wb;
-        wb.w_u = __shfl_sync(0xffffffffu, w.w_u, src);
-        wb.w_r = __shfl_sync(0xffffffffu, w.w_r, src);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) wb.wt[i] = __shfl_sync(0xffffffffu, w.wt[i], src);
-        double xb[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) xb[i] = __shfl_sync(0xffffffffu, x_cur[i], src);
-        const double lam_b = __shfl_sync(0xffffffffu, lambda, src);
-        const double sp_b = __shfl_sync(0xffffffffu, set_point, src);
-        const double target_b[4] = {sp_b, half_pi, 0.0, 0.0};
-        Ctx cw;
-        cw.cfg = c.cfg;
-        cw.sm = c.sm + (ptrdiff_t)(g_src - g_mine) * k.stride;
-        cw.kk = c.kk + (ptrdiff_t)(g_src - g_mine) * k.kk_stride;
-        cw.gl = lane;
-        cw.gmask = 0xffffffffu;
-        double cdx_w = 0.0;
-        const bool ok_w = riccati_qp<32>(cw, wb, lam_b, xb, target_b, cdx_w);
-        cdx_w = group_sum<32>(cdx_w, 0xffffffffu);
-        if (g_mine == g_src) {
-          qp_ok = ok_w;
-          cdx = (c.gl == 0) ? cdx_w : 0.0;
-        }
-        need_mask &= ~((((L == 32) ? 0u : (1u << L)) - 1u) << (g_src * L));
-        __syncwarp(0xffffffffu);
-      }
-    } else {
-      if (need_riccati) qp_ok = riccati_qp<L>(c, w, lambda, x_cur, target, cdx);
-    }
+    CPMPC_MARK(2);
+    if (need_riccati) qp_ok = riccati_qp<L>(c, w, lambda, x_cur, target, cdx);
+    CPMPC_MARK(3);
     if (active) {
       if (dbg != nullptr) {
         // debug view: the blocks of this linearisation and the QP step, then stop (the candidates would overwrite Gam)
@@ -1345,6 +1217,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
       }
     }
 
+    CPMPC_MARK(4);
     // ---- line search (nonlinear.cc:351-443), groups of the warp in lock step ---------------------------------------
     double& phi0 = cold.phi0;
     double& dphi0 = cold.dphi0;
@@ -1443,6 +1316,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
       }
     }
 
+    CPMPC_MARK(5);
     // ---- lambda update and exit tests (nonlinear.cc:296-343) -------------------------------------------------------
     if (active) {
       bool exit_now = false;
@@ -1495,7 +1369,9 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
       }
       if (exit_now) active = false;
     }
+    CPMPC_MARK(6);
   }
+#undef CPMPC_MARK
   res.opt_state = opt_state;
   res.f = cur_f;
   res.eq = cur_eq;
@@ -1530,11 +1406,20 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
   // trials) go on instead of idling until the slowest warp of a static round is done.  Warp-wide votes stay
   // convergent because all groups of a warp enter and leave a batch together.
   const long long t_begin = clock64();
+  unsigned long long last_base = ~0ull;
+  struct WarpPhases {
+    long long ph[N_PHASES + 1];
+  } wph;
+  asm volatile("" : : "l"(&wph) : "memory");
+#pragma unroll
+  for (int i = 0; i < N_PHASES; ++i) wph.ph[i] = 0;
+  wph.ph[N_PHASES] = t_begin;
   for (;;) {
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(io.queue, (unsigned long long)G);
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base >= (unsigned long long)io.B) break;
+    last_base = base;
     const long long inst = (long long)base + g;
     const bool have = inst < io.B;
 
@@ -1546,6 +1431,7 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
       long long solves, sum_iter, sum_ls, sum_bad;
       SolveResult res;
     } kc;
+    long long* ph = wph.ph;
     asm volatile("" : : "l"(&kc) : "memory");
     Weights& w = kc.w;
     double(&x_cur)[4] = kc.x_cur;
@@ -1632,7 +1518,12 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
                          ? io.iter_log + (size_t)inst * cfg.max_iter * CPMPC_ITERLOG_STRIDE
                          : nullptr;
       double* dbg = (io.dbg != nullptr && have) ? io.dbg + (size_t)inst * io.dbg_stride : nullptr;
-      solve_group<L>(c, have, w, x_cur, set_point, u_prev, ilog, res, dbg, io.dbg_lambda, io.dbg_qp);
+      {
+        const long long now = clock64();
+        ph[0] += now - ph[N_PHASES];
+        ph[N_PHASES] = now;
+      }
+      solve_group<L>(c, have, w, x_cur, set_point, u_prev, ilog, res, ph, dbg, io.dbg_lambda, io.dbg_qp);
 
       if (have) {
         // ---- outputs (optimization.cc:83-96) ------------------------------------------------------------------
@@ -1711,6 +1602,11 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
         }
         CPMPC_GSYNC();
       }
+      {
+        const long long now = clock64();
+        ph[7] += now - ph[N_PHASES];
+        ph[N_PHASES] = now;
+      }
     }
     if (have && c.gl == 0) {
       if (io.sim) {
@@ -1729,7 +1625,11 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
   // the last warp to drain the queue re-arms it for the next launch on this handle (launches are stream-ordered)
   if (lane == 0) {
     if (io.warp_cycles != nullptr) {
-      io.warp_cycles[(size_t)blockIdx.x * WARPS_PER_BLOCK + warp] = (unsigned long long)(clock64() - t_begin);
+      unsigned long long* rec = io.warp_cycles + (size_t)WARP_REC * ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
+      rec[0] = (unsigned long long)(clock64() - t_begin);
+      rec[1] = last_base;
+#pragma unroll
+      for (int i = 0; i < N_PHASES; ++i) rec[2 + i] = (unsigned long long)wph.ph[i];
     }
     __threadfence();
     const unsigned long long total = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;

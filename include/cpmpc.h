@@ -184,9 +184,14 @@ int64_t cpmpc_debug_stride(cpmpc_handle h);
 int cpmpc_debug_first_qp(cpmpc_handle h, const double* states, const double* dyn_params, const double* set_points,
                          const double* weights, double lambda, int qp_method, double* blocks_out);
 
-/* SM cycles (clock64) every warp of the LAST launch on this handle spent on its instances: names the straggler warp
- * when a launch is one wave of warps and its duration is the slowest warp's (bench.py per_rank).  Synchronises the
- * device.  Returns the number of warps; writes nothing when cycles_out is NULL or capacity is too small; -1 on error. */
+/* Per warp of the LAST launch on this handle, CPMPC_WARP_RECORD values: the SM cycles (clock64) it spent on its
+ * instances, the first instance of the last batch it drew from the work queue, and the cycles per solver phase
+ * (set-up + initial guess, linearisation, condensed QP, Riccati recursion, directional derivatives + penalty, line
+ * search, update / exit tests, outputs).  Names the straggler warp, the instances it carried and where its time went
+ * when a launch is one wave of warps and its duration is the slowest warp's (bench.py per_rank).
+ * Synchronises the device.  cycles_out: HOST [CPMPC_WARP_RECORD * warps]; `capacity` counts warps.  Returns the number of warps; writes
+ * nothing when cycles_out is NULL or capacity is too small; -1 on error. */
+#define CPMPC_WARP_RECORD 10
 int64_t cpmpc_get_warp_cycles(cpmpc_handle h, uint64_t* cycles_out, int64_t capacity);
 
 /* Number of kernel launches issued by this library since load (for bench accounting). */

@@ -18,7 +18,7 @@ from cart_pole_mpc_b200 import BatchedOptimization, _capi, synthetic  # noqa: E4
 
 
 def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+    n = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 8
     B = 4096
     dev = torch.device("cuda:0")
     solver = BatchedOptimization(B, device=0)
@@ -40,8 +40,29 @@ def main():
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         s = np.frombuffer(stats.cpu().numpy().tobytes(), dtype=np.dtype(_capi.STATS_DTYPE))
-        wc = solver.warp_cycles().astype(np.float64)
-        wc = wc[wc > 0]
+        wci = solver.warp_cycles(with_instances=True)
+        wci = wci[wci[:, 0] > 0]
+        wc = wci[:, 0].astype(np.float64)
+        worst = int(wci[np.argmax(wc), 1])
+        if "--why" in sys.argv:
+            med = np.median(wci[:, 2:].astype(np.float64), axis=0)
+            top = wci[np.argmax(wc), 2:].astype(np.float64)
+            print(json.dumps({"shard": shard, "phase_kcycles": {nm: [round(m / 1e3, 1), round(t / 1e3, 1)] for nm, m, t in
+                                                                 zip(BatchedOptimization.PHASE_NAMES, med, top)},
+                              "columns": "[median warp, slowest warp]"}))
+        if "--why" in sys.argv and wc.max() > 1.2 * np.median(wc):
+            solver.enable_iteration_log(True)
+            solver.reset_device()
+            solver.step_device(std, dyd, spd, u, pred_out=pred, stats_out=stats)
+            torch.cuda.synchronize()
+            log = solver.get_iteration_log()
+            for i in range(worst, min(worst + 8, B)):
+                it = int(s["n_iterations"][i])
+                print(json.dumps({"instance": i, "iterations": it, "merit_evals": [int(v) for v in log[i, :it, 8]],
+                                  "step_results": [int(v) for v in log[i, :it, 7]],
+                                  "lambda": [float(v) for v in log[i, :it, 1]],
+                                  "state": [round(float(v), 3) for v in st[i]], "m_b,m_1": [round(float(v), 3) for v in dy[i, :2]]}))
+            solver.enable_iteration_log(False)
         rows.append({"shard": shard, "ms": round(float(np.median(ts[3:])), 4),
                      "slowest_warp_kcycles": round(float(wc.max()) / 1e3, 1),
                      "median_warp_kcycles": round(float(np.median(wc)) / 1e3, 1),

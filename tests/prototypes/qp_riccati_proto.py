@@ -278,6 +278,116 @@ def riccati(Phi, Gam, ev, xs, u, x_cur, set_point, u_prev, wts, lam, W, S):
     return np.concatenate([dx, du])
 
 
+def riccati_knot(Phi, Gam, ev, xs, u, x_cur, set_point, u_prev, wts, lam, W, S):
+    """Knot-level Riccati recursion in end-of-segment coordinates (round 2): one SCALAR control per step.
+
+    Inside segment s the state is z = (y, p): y = Phi_s dx_s + e_s + sum_{j<i} Gam_s[:, j] v_j (the segment's end state
+    as far as it is determined by the controls already applied) and p = the previous control.  One knot:
+        z+ = A z + b v,  A = diag(1,1,1,1,0),  b = (Gam_s[:, i], 1),
+        cost = 1/2 (wu2 + lam) v^2 + 1/2 wr2 (v - p)^2 + g_i v
+    so every elimination is a scalar pivot  s = wu2 + lam + wr2 + b^T P b  and the value function over (z | rho) stays
+    a (5 + nr) x (5 + nr) matrix (rho = affine coordinate + one multiplier per hard terminal row).  At a shooting node
+    the value function is pulled back through y = Phi dx + e."""
+    w_u, w_r, wt = wts[0], wts[1], wts[2:]
+    nseg = W // S
+    NS = nseg + 1
+    target = np.array([set_point, math.pi / 2, 0.0, 0.0])
+    wu2, wr2 = w_u ** 2, w_r ** 2
+    g = np.zeros(W)
+    for k in range(W):
+        g[k] = wu2 * u[k]
+        if k + 1 < W:
+            g[k] += wr2 * (u[k] - u[k + 1])
+        if k > 0:
+            g[k] -= wr2 * (u[k - 1] - u[k])
+        if k == 0:
+            g[k] += wr2 * (u[k] - u_prev)
+    dT = xs[NS - 1] - target
+    dT[1] = wrap(dT[1])
+    hard = [i for i in range(4) if wt[i] < 0]
+    nr = 1 + len(hard)
+    P = np.zeros((5, 5))
+    Q = np.zeros((5, nr))
+    C = np.zeros((nr, nr))
+    for i in range(4):
+        P[i, i] = lam
+        if wt[i] >= 0:
+            P[i, i] += wt[i] ** 2
+            Q[i, 0] = wt[i] ** 2 * dT[i]
+    for j, i in enumerate(hard):
+        Q[i, 1 + j] = 1.0
+    kz = np.zeros((W, 5))
+    kr = np.zeros((W, nr))
+    for s in range(nseg - 1, -1, -1):
+        for i in range(S - 1, -1, -1):
+            k = s * S + i
+            b = np.array([Gam[s][0, i], Gam[s][1, i], Gam[s][2, i], Gam[s][3, i], 1.0])
+            Pb = P @ b
+            # the rate cost between v_k and its successor is carried by P[4,4] / Q (added when the successor was eliminated);
+            # here: own cost + the rate term towards the PREVIOUS control p (also for k = 0: towards the applied control,
+            # whose linear part is already in g[0])
+            piv = wu2 + lam + wr2 + b @ Pb
+            if not piv > 0:
+                raise FloatingPointError("indefinite")
+            rz = np.array([Pb[0], Pb[1], Pb[2], Pb[3], -wr2 if k > 0 else 0.0])
+            rr = Q.T @ b
+            rr[0] += g[k]
+            inv = 1.0 / piv
+            kz[k] = rz * inv
+            kr[k] = rr * inv
+            Pn = P.copy()
+            Pn[4, :] = 0.0
+            Pn[:, 4] = 0.0
+            Pn[4, 4] = wr2 if k > 0 else 0.0
+            P = Pn - np.outer(rz, rz) * inv
+            Qn = Q.copy()
+            Qn[4, :] = 0.0
+            Q = Qn - np.outer(rz, rr) * inv
+            C = C - np.outer(rr, rr) * inv
+        # node s: y = Phi dx + e rho_0, p unchanged; lambda on dx_s (not on the fixed dx_0)
+        F = np.eye(5)
+        F[:4, :4] = Phi[s]
+        f = np.zeros(5)
+        f[:4] = ev[s]
+        Pf = P @ f
+        C[0, :] += f @ Q
+        C[:, 0] += f @ Q
+        C[0, 0] += f @ Pf
+        Q[:, 0] += Pf
+        Q = F.T @ Q
+        P = F.T @ P @ F
+        if s > 0:
+            for i in range(4):
+                P[i, i] += lam
+    d0 = xs[0] - x_cur
+    d0[1] = wrap(d0[1])
+    m0 = -d0
+    coef = np.zeros(nr)
+    coef[0] = 1.0
+    if hard:
+        # stationarity in the multipliers: Q[:4, 1+j] . m0 + C[1+j, 0] + sum_q C[1+j, 1+q] mu_q + dT_j = 0
+        nh = len(hard)
+        Mh = -C[1:, 1:]
+        rhs = np.array([Q[:4, 1 + j] @ m0 + C[1 + j, 0] + dT[hard[j]] for j in range(nh)])
+        coef[1:] = np.linalg.solve(Mh, rhs)
+    dx = [m0]
+    du = np.zeros(W)
+    p = 0.0
+    x = m0
+    for s in range(nseg):
+        y = Phi[s] @ x + ev[s]
+        for i in range(S):
+            k = s * S + i
+            z = np.array([y[0], y[1], y[2], y[3], p])
+            v = -(kz[k] @ z + kr[k] @ coef)
+            y = y + Gam[s][:, i] * v
+            p = v
+            du[k] = v
+        x = y
+        dx.append(x)
+    return np.concatenate([np.concatenate(dx), du])
+
+
 def iterate_point(dyn, x0, W, S, dt, n_newton, wts, set_point):
     """A realistic linearisation point: cold-start guess, then n_newton full QP steps (alpha = 0.5) with retraction."""
     nseg = W // S
@@ -325,6 +435,7 @@ def main():
         if args.lam == 0.0:
             out["condensed"] = np.abs(condensed(Phi, Gam, ev, xs, u, states[i], sp[i], 0.0, wts, 0.0, W, S) - truth).max() / scale
         out["riccati"] = np.abs(riccati(Phi, Gam, ev, xs, u, states[i], sp[i], 0.0, wts, args.lam, W, S) - truth).max() / scale
+        out["riccati_knot"] = np.abs(riccati_knot(Phi, Gam, ev, xs, u, states[i], sp[i], 0.0, wts, args.lam, W, S) - truth).max() / scale
         print(i, f"|dx|max {scale:.3e}", {k: f"{v:.2e}" for k, v in out.items()})
 
 
