@@ -750,7 +750,33 @@ def main():
     for _ in range(e2e_steps):
         one_e2e()
     torch.cuda.synchronize()
+    e2e_sync_s = time.perf_counter() - t0
+
+    # the same through the pipelined entry points (cpmpc_step_async / cpmpc_wait, two steps in flight, two sets of
+    # pinned output buffers): every step still copies its inputs in and ALL its results out, but the device-to-host copy
+    # of step k overlaps the kernel of step k + 1.  Each step is a cold start (CPMPC_STEP_RESET), like above.
+    outs = [(u_p, pred_p, stats_p),
+            (torch.empty((B, W), dtype=torch.float64).pin_memory(), torch.empty((B, W, 4), dtype=torch.float64).pin_memory(),
+             torch.empty((B, 56), dtype=torch.uint8).pin_memory())]
+
+    def e2e_pipelined(n):
+        for i in range(n):
+            uo, po, so = outs[i & 1]
+            _capi.check(lib.cpmpc_step_async(solver._h, st_p.data_ptr(), dy_p.data_ptr(), sp_p.data_ptr(), None,
+                                             uo.data_ptr(), po.data_ptr(), so.data_ptr(), 1))
+            if i > 0:
+                _capi.check(lib.cpmpc_wait(solver._h))  # retires step i - 1: its outputs are now complete
+        _capi.check(lib.cpmpc_wait(solver._h))
+
+    e2e_pipelined(4)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e2e_pipelined(e2e_steps)
     e2e_s = time.perf_counter() - t0
+    e2e_equal = bool(np.array_equal(outs[0][0].numpy(), outs[1][0].numpy()) and
+                     np.array_equal(outs[0][0].numpy(), u_d.cpu().numpy()))
     h2d = B * (4 + 9 + 1) * 8
     d2h = B * (W + 4 * W) * 8 + B * 56
 
@@ -809,9 +835,9 @@ def main():
                             "rank's step time is the latency of its hardest warp; the max over ranks is reported"}
         all_reasons = sorted({r for rs in per_rank["throttle_reasons"] for r in rs})
         clocks = dict(clocks, reasons=all_reasons, sm_mhz_min_over_ranks=min(per_rank["sm_mhz"]))
-        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+        t = torch.tensor([total_ms, e2e_s, e2e_sync_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s = float(t[0]), float(t[1])
+        total_ms, e2e_s, e2e_sync_s = float(t[0]), float(t[1]), float(t[2])
         w = torch.tensor([flops_step, n_iter_sum, n_ls_sum], dtype=torch.float64, device=dev)
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
         flops_step_all = float(w[0])
@@ -866,7 +892,12 @@ def main():
         "config": headline_config(B, gathered_u is not None),
         "env_knobs": env_knobs(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "path": "cpmpc_step: pinned host buffers -> H2D -> kernel -> D2H"},
+                "steps": e2e_steps,
+                "path": "cpmpc_step_async / cpmpc_wait: pinned host buffers -> H2D -> kernel -> D2H every step, two "
+                        "steps in flight (the D2H of step k overlaps the kernel of step k + 1)",
+                "results_equal_device_resident_arm": e2e_equal,
+                "synchronous": {"value": world * B * e2e_steps / e2e_sync_s, "unit": UNIT,
+                                "path": "cpmpc_step: one step at a time, H2D -> kernel -> D2H, nothing overlapped"}},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",

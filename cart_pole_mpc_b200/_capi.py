@@ -17,7 +17,7 @@ FLAG_MIN_LATENCY = 2  # CPMPC_FLAG_MIN_LATENCY
 
 EXPORTED_SYMBOLS = (
     "cpmpc_last_error", "cpmpc_version", "cpmpc_default_params", "cpmpc_create", "cpmpc_create_ex", "cpmpc_destroy", "cpmpc_batch",
-    "cpmpc_solution_dim", "cpmpc_step", "cpmpc_step_device", "cpmpc_reset", "cpmpc_reset_device",
+    "cpmpc_solution_dim", "cpmpc_step", "cpmpc_step_async", "cpmpc_wait", "cpmpc_step_device", "cpmpc_reset", "cpmpc_reset_device",
     "cpmpc_set_previous_solution",
     "cpmpc_get_previous_solution", "cpmpc_enable_iteration_log", "cpmpc_get_iteration_log", "cpmpc_sim_step_device",
     "cpmpc_sim_step", "cpmpc_closed_loop", "cpmpc_closed_loop_device", "cpmpc_launch_count",
@@ -128,6 +128,10 @@ def lib() -> C.CDLL:
     # pointers are passed as void* so both numpy (host) and torch data_ptr() (device) addresses can be given
     L.cpmpc_step.restype = C.c_int
     L.cpmpc_step.argtypes = [vp] * 8
+    L.cpmpc_step_async.restype = C.c_int
+    L.cpmpc_step_async.argtypes = [vp] * 8 + [C.c_uint32]
+    L.cpmpc_wait.restype = C.c_int
+    L.cpmpc_wait.argtypes = [vp]
     L.cpmpc_step_device.restype = C.c_int
     L.cpmpc_step_device.argtypes = [vp] * 9
     L.cpmpc_reset.restype = C.c_int

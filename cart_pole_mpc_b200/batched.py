@@ -108,6 +108,27 @@ class BatchedOptimization:
             pred.ctypes.data if pred is not None else None, stats.ctypes.data))
         return StepOutputs(u, pred, stats)
 
+    # ---- pipelined host-buffer path ---------------------------------------------------------------------------------
+    def step_async(self, states, dyn_params, set_points, u_out, weights=None, pred_out=None, stats_out=None,
+                   reset: bool = False) -> None:
+        """cpmpc_step_async: enqueue one Step over caller-owned (ideally pinned) host arrays and return; at most two
+        steps are in flight.  The arrays must stay alive and untouched until the `wait()` that retires the step.
+        `reset=True` makes it a cold start (Reset() ordered before the solve)."""
+        B, W = self.batch, self.W
+        for name, a, shape in (("states", states, (B, 4)), ("dyn_params", dyn_params, (B, 9)),
+                               ("set_points", set_points, (B,)), ("u_out", u_out, (B, W))):
+            if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.shape == shape):
+                raise ValueError(f"{name} must be a C-contiguous float64 array of shape {shape}")
+        _capi.check(self._lib.cpmpc_step_async(
+            self._h, states.ctypes.data, dyn_params.ctypes.data, set_points.ctypes.data,
+            weights.ctypes.data if weights is not None else None, u_out.ctypes.data,
+            pred_out.ctypes.data if pred_out is not None else None,
+            stats_out.ctypes.data if stats_out is not None else None, 1 if reset else 0))
+
+    def wait(self) -> None:
+        """cpmpc_wait: block until the oldest step in flight is complete."""
+        _capi.check(self._lib.cpmpc_wait(self._h))
+
     # ---- device-pointer path (torch tensors on this device, float64, contiguous) ----------------------------------
     def step_device(self, states, dyn_params, set_points, u_out, weights=None, pred_out=None, stats_out=None,
                     stream=None) -> None:

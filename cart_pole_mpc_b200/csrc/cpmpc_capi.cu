@@ -85,6 +85,19 @@ struct cpmpc_solver {
   // cpmpc_reset_device runs on the caller's stream; the host-buffer entry points run on `stream` and wait for it
   cudaEvent_t reset_event = nullptr;
   bool reset_pending = false;
+  // cpmpc_step_async / cpmpc_wait: two slots, each with its own stream and staging buffers, so that the device-to-host
+  // copy of step k overlaps the host-to-device copy and the kernel of step k + 1 (the kernels themselves are chained
+  // by `kernel_done`: they share the warm start, the work queue and the Riccati scratch)
+  struct AsyncSlot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t kernel_done = nullptr, all_done = nullptr;
+    double *d_states = nullptr, *d_dyn = nullptr, *d_sp = nullptr, *d_weights = nullptr, *d_u = nullptr, *d_pred = nullptr;
+    cpmpc_stats* d_stats = nullptr;
+    bool busy = false;
+  } slot[2];
+  int next_slot = 0;      // slot the next cpmpc_step_async uses
+  int in_flight = 0;      // 0..2
+  cudaEvent_t last_kernel_done = nullptr;  // of the most recent asynchronous step (not owned: points into a slot)
 };
 
 namespace {
@@ -182,6 +195,55 @@ int EnsureStaging(cpmpc_solver* h) {
     }
   }
   return rc;
+}
+
+int EnsureSlot(cpmpc_solver* h, cpmpc_solver::AsyncSlot& sl) {
+  if (sl.d_stats != nullptr) return CPMPC_OK;  // the last one allocated
+  const long long B = h->B;
+  const int W = h->cfg.W;
+  auto alloc_all = [&]() -> int {
+    if (sl.stream == nullptr) CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    if (sl.kernel_done == nullptr) CUDA_TRY(cudaEventCreateWithFlags(&sl.kernel_done, cudaEventDisableTiming));
+    if (sl.all_done == nullptr) CUDA_TRY(cudaEventCreateWithFlags(&sl.all_done, cudaEventDisableTiming));
+    CUDA_TRY(cudaMalloc(&sl.d_states, sizeof(double) * B * 4));
+    CUDA_TRY(cudaMalloc(&sl.d_dyn, sizeof(double) * B * 9));
+    CUDA_TRY(cudaMalloc(&sl.d_sp, sizeof(double) * B));
+    CUDA_TRY(cudaMalloc(&sl.d_weights, sizeof(double) * B * CPMPC_WEIGHTS_STRIDE));
+    CUDA_TRY(cudaMalloc(&sl.d_u, sizeof(double) * B * W));
+    CUDA_TRY(cudaMalloc(&sl.d_pred, sizeof(double) * B * W * 4));
+    CUDA_TRY(cudaMalloc(&sl.d_stats, sizeof(cpmpc_stats) * B));
+    return CPMPC_OK;
+  };
+  const int rc = alloc_all();
+  if (rc != CPMPC_OK) {
+    for (void** p : {reinterpret_cast<void**>(&sl.d_states), reinterpret_cast<void**>(&sl.d_dyn),
+                     reinterpret_cast<void**>(&sl.d_sp), reinterpret_cast<void**>(&sl.d_weights),
+                     reinterpret_cast<void**>(&sl.d_u), reinterpret_cast<void**>(&sl.d_pred),
+                     reinterpret_cast<void**>(&sl.d_stats)}) {
+      cudaFree(*p);
+      *p = nullptr;
+    }
+  }
+  return rc;
+}
+
+// Waits for the oldest asynchronous step in flight (no-op when there is none).
+int WaitOldest(cpmpc_solver* h) {
+  if (h->in_flight == 0) return CPMPC_OK;
+  const int oldest = (h->next_slot + 2 - h->in_flight) % 2;
+  cpmpc_solver::AsyncSlot& sl = h->slot[oldest];
+  const cudaError_t e = cudaEventSynchronize(sl.all_done);
+  sl.busy = false;
+  h->in_flight -= 1;
+  if (e != cudaSuccess) return Fail(CPMPC_ERR_CUDA, std::string("cpmpc_wait: ") + cudaGetErrorString(e));
+  return CPMPC_OK;
+}
+
+int DrainAsync(cpmpc_solver* h) {
+  while (h->in_flight > 0) {
+    if (int rc = WaitOldest(h)) return rc;
+  }
+  return CPMPC_OK;
 }
 
 // Orders the handle's own stream behind a cpmpc_reset_device issued on another stream.
@@ -487,6 +549,19 @@ int cpmpc_destroy(cpmpc_handle h) {
   cudaFree(h->d_controls);
   cudaFree(h->d_pack);
   if (h->h_pack) cudaFreeHost(h->h_pack);
+  for (cpmpc_solver::AsyncSlot& sl : h->slot) {
+    if (sl.stream) cudaStreamSynchronize(sl.stream);
+    cudaFree(sl.d_states);
+    cudaFree(sl.d_dyn);
+    cudaFree(sl.d_sp);
+    cudaFree(sl.d_weights);
+    cudaFree(sl.d_u);
+    cudaFree(sl.d_pred);
+    cudaFree(sl.d_stats);
+    if (sl.kernel_done) cudaEventDestroy(sl.kernel_done);
+    if (sl.all_done) cudaEventDestroy(sl.all_done);
+    if (sl.stream) cudaStreamDestroy(sl.stream);
+  }
   if (h->reset_event) cudaEventDestroy(h->reset_event);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -525,6 +600,7 @@ int cpmpc_step(cpmpc_handle h, const double* states, const double* dyn_params, c
     return Fail(CPMPC_ERR_INVALID_ARGUMENT, "states, dyn_params, set_points and u_out are required");
   }
   CUDA_TRY(cudaSetDevice(h->device));
+  if (int rc = DrainAsync(h)) return rc;
   if (int rc = WaitForReset(h)) return rc;
   if (h->B <= kPackedBatchMax) return StepPacked(h, states, dyn_params, set_points, weights, u_out, pred_out, stats_out);
   if (int rc = EnsureStaging(h)) return rc;
@@ -553,9 +629,67 @@ int cpmpc_step(cpmpc_handle h, const double* states, const double* dyn_params, c
   return CPMPC_OK;
 }
 
+int cpmpc_step_async(cpmpc_handle h, const double* states, const double* dyn_params, const double* set_points,
+                     const double* weights, double* u_out, double* pred_out, cpmpc_stats* stats_out, uint32_t flags) {
+  if (h == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "null handle");
+  if (states == nullptr || dyn_params == nullptr || set_points == nullptr || u_out == nullptr) {
+    return Fail(CPMPC_ERR_INVALID_ARGUMENT, "states, dyn_params, set_points and u_out are required");
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (h->in_flight == 2) {
+    if (int rc = WaitOldest(h)) return rc;  // both slots taken: the oldest step has to finish first
+  }
+  cpmpc_solver::AsyncSlot& sl = h->slot[h->next_slot];
+  if (int rc = EnsureSlot(h, sl)) return rc;
+  const long long B = h->B;
+  const int W = h->cfg.W;
+  cudaStream_t s = sl.stream;
+  // inputs: may overlap the previous step's kernel and its device-to-host copy
+  CUDA_TRY(cudaMemcpyAsync(sl.d_states, states, sizeof(double) * B * 4, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(sl.d_dyn, dyn_params, sizeof(double) * B * 9, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(sl.d_sp, set_points, sizeof(double) * B, cudaMemcpyHostToDevice, s));
+  if (weights != nullptr) {
+    CUDA_TRY(cudaMemcpyAsync(sl.d_weights, weights, sizeof(double) * B * CPMPC_WEIGHTS_STRIDE, cudaMemcpyHostToDevice, s));
+  }
+  // the kernel: after everything that touches the warm start (previous asynchronous kernel, synchronous calls on the
+  // handle's own stream, a reset issued on a caller stream)
+  if (h->last_kernel_done != nullptr) CUDA_TRY(cudaStreamWaitEvent(s, h->last_kernel_done, 0));
+  if (h->reset_pending) {
+    CUDA_TRY(cudaStreamWaitEvent(s, h->reset_event, 0));
+    h->reset_pending = false;
+  }
+  if ((flags & CPMPC_STEP_RESET) != 0u) CUDA_TRY(cudaMemsetAsync(h->d_has_prev, 0, h->B, s));
+  if (int rc = cpmpc_step_device(h, sl.d_states, sl.d_dyn, sl.d_sp, weights ? sl.d_weights : nullptr, sl.d_u,
+                                 pred_out ? sl.d_pred : nullptr, stats_out ? sl.d_stats : nullptr, s)) {
+    return rc;
+  }
+  CUDA_TRY(cudaEventRecord(sl.kernel_done, s));
+  h->last_kernel_done = sl.kernel_done;
+  // results: overlap the next step's copy-in and kernel
+  CUDA_TRY(cudaMemcpyAsync(u_out, sl.d_u, sizeof(double) * B * W, cudaMemcpyDeviceToHost, s));
+  if (pred_out != nullptr) {
+    CUDA_TRY(cudaMemcpyAsync(pred_out, sl.d_pred, sizeof(double) * B * W * 4, cudaMemcpyDeviceToHost, s));
+  }
+  if (stats_out != nullptr) {
+    CUDA_TRY(cudaMemcpyAsync(stats_out, sl.d_stats, sizeof(cpmpc_stats) * B, cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_TRY(cudaEventRecord(sl.all_done, s));
+  sl.busy = true;
+  h->in_flight += 1;
+  h->next_slot ^= 1;
+  return CPMPC_OK;
+}
+
+int cpmpc_wait(cpmpc_handle h) {
+  if (h == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  return WaitOldest(h);
+}
+
 int cpmpc_reset(cpmpc_handle h, const uint8_t* mask) {
   if (h == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "null handle");
   CUDA_TRY(cudaSetDevice(h->device));
+  if (int rc = DrainAsync(h)) return rc;
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   if (mask == nullptr) {
     CUDA_TRY(cudaMemset(h->d_has_prev, 0, h->B));
@@ -583,6 +717,7 @@ int cpmpc_reset_device(cpmpc_handle h, void* stream) {
 int cpmpc_set_previous_solution(cpmpc_handle h, const double* solutions, const uint8_t* mask) {
   if (h == nullptr || solutions == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "null argument");
   CUDA_TRY(cudaSetDevice(h->device));
+  if (int rc = DrainAsync(h)) return rc;
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   const int N = h->cfg.N;
   if (mask == nullptr) {
@@ -605,6 +740,7 @@ int cpmpc_set_previous_solution(cpmpc_handle h, const double* solutions, const u
 int cpmpc_get_previous_solution(cpmpc_handle h, double* solutions_out, uint8_t* has_prev_out) {
   if (h == nullptr || solutions_out == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "null argument");
   CUDA_TRY(cudaSetDevice(h->device));
+  if (int rc = DrainAsync(h)) return rc;
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   CUDA_TRY(cudaMemcpy(solutions_out, h->d_prev, sizeof(double) * h->B * h->cfg.N, cudaMemcpyDeviceToHost));
   if (has_prev_out != nullptr) {
@@ -629,6 +765,7 @@ int cpmpc_get_iteration_log(cpmpc_handle h, double* log_out) {
   if (h == nullptr || log_out == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "null argument");
   if (h->d_iter_log == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "iteration log was never enabled");
   CUDA_TRY(cudaSetDevice(h->device));
+  if (int rc = DrainAsync(h)) return rc;
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   CUDA_TRY(cudaMemcpy(log_out, h->d_iter_log, sizeof(double) * h->B * h->cfg.max_iter * CPMPC_ITERLOG_STRIDE,
                       cudaMemcpyDeviceToHost));
@@ -719,6 +856,7 @@ int cpmpc_closed_loop(cpmpc_handle h, int64_t n_steps, double* states, const dou
     return Fail(CPMPC_ERR_INVALID_ARGUMENT, "n_steps >= 1, states, dyn_params and set_points are required");
   }
   CUDA_TRY(cudaSetDevice(h->device));
+  if (int rc = DrainAsync(h)) return rc;
   if (int rc = WaitForReset(h)) return rc;
   if (int rc = EnsureStaging(h)) return rc;
   const long long B = h->B;
@@ -784,6 +922,7 @@ int cpmpc_debug_first_qp(cpmpc_handle h, const double* states, const double* dyn
     return Fail(CPMPC_ERR_UNSUPPORTED, "this handle has no scratch for the condensed form (long horizon: W * dt > 0.6 s)");
   }
   CUDA_TRY(cudaSetDevice(h->device));
+  if (int rc = DrainAsync(h)) return rc;
   if (int rc = WaitForReset(h)) return rc;
   if (int rc = EnsureStaging(h)) return rc;
   const long long B = h->B;

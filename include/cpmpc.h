@@ -124,6 +124,22 @@ int64_t cpmpc_solution_dim(cpmpc_handle h); /* N */
 int cpmpc_step(cpmpc_handle h, const double* states, const double* dyn_params, const double* set_points,
                const double* weights, double* u_out, double* pred_out, cpmpc_stats* stats_out);
 
+/* Pipelined variant of cpmpc_step for callers that issue step after step (a controller farm, the benchmark): the call
+ * returns as soon as the work is enqueued, and up to TWO steps may be in flight, so that the device-to-host copy of
+ * step k overlaps the host-to-device copy and the kernel of step k + 1 (the kernels themselves run one after the
+ * other: step k + 1 warm-starts from step k, exactly as consecutive Optimization::Step calls do).
+ *   - buffers are as for cpmpc_step and should be PINNED host memory (pageable memory makes the copies synchronous);
+ *     inputs and outputs of a step must stay untouched until the cpmpc_wait that retires it;
+ *   - cpmpc_wait blocks until the OLDEST step in flight has finished and its outputs are complete (no-op when
+ *     nothing is in flight); a third cpmpc_step_async first waits for the oldest one itself;
+ *   - flags: CPMPC_STEP_RESET = Optimization::Reset() of every instance, ordered before this step's solve;
+ *   - every synchronous entry point of the handle (cpmpc_step, cpmpc_reset, cpmpc_get_previous_solution, ...)
+ *     retires all steps in flight first. */
+#define CPMPC_STEP_RESET 1u
+int cpmpc_step_async(cpmpc_handle h, const double* states, const double* dyn_params, const double* set_points,
+                     const double* weights, double* u_out, double* pred_out, cpmpc_stats* stats_out, uint32_t flags);
+int cpmpc_wait(cpmpc_handle h);
+
 /* Same, with DEVICE pointers (on the handle's device), asynchronous on `stream` (a cudaStream_t, may be NULL for
  * the default stream).  The caller synchronises. */
 int cpmpc_step_device(cpmpc_handle h, const double* states, const double* dyn_params, const double* set_points,

@@ -767,3 +767,47 @@ def test_native_pypendulum_runs_scratch_py(oracle):
         bad = pp.OptimizationParams()
         bad.state_spacing = 7
         pp.Optimization(bad)
+
+
+def test_pipelined_steps_equal_synchronous_steps():
+    """cpmpc_step_async / cpmpc_wait (two steps in flight, D2H of step k overlapping the kernel of step k + 1): the
+    same bits as cpmpc_step, for a chain of warm-started steps, for cold steps via CPMPC_STEP_RESET, and when
+    synchronous calls are mixed in (they retire the steps in flight first)."""
+    import torch
+    from cart_pole_mpc_b200 import synthetic, _capi
+    B, W, T = 512, 40, 5
+    st, dy, sp = synthetic.swingup_batch(B, seed=6)
+    states = [st + 0.01 * t for t in range(T)]
+    ref = _solver(B)
+    want = [ref.step(states[t], dy, sp) for t in range(T)]           # warm-started chain, one step at a time
+    cold = _solver(B).step(states[2], dy, sp)
+
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    s = _solver(B)
+    ins = [pin(x) for x in states]
+    dyp, spp = pin(dy), pin(sp)
+    u = [pin(np.zeros((B, W))) for _ in range(T)]
+    pred = [pin(np.zeros((B, W, 4))) for _ in range(T)]
+    stats = [pin(np.zeros(B, dtype=_capi.STATS_DTYPE).view(np.uint8)) for _ in range(T)]
+    for t in range(T):
+        s.step_async(ins[t], dyp, spp, u[t], pred_out=pred[t], stats_out=stats[t])
+        if t > 0:
+            s.wait()
+    s.wait()
+    s.wait()  # nothing in flight: no-op
+    for t in range(T):
+        assert np.array_equal(u[t], want[t].u), t
+        assert np.array_equal(pred[t], want[t].predicted_states), t
+        assert np.array_equal(stats[t].view(_capi.STATS_DTYPE), want[t].stats), t
+    # cold steps through the flag, without waiting in between (the third call retires the first by itself)
+    for t in range(3):
+        s.step_async(ins[2], dyp, spp, u[t], reset=True)
+    sol, has = s.get_previous_solution()       # a synchronous call: retires everything in flight first
+    assert has.all()
+    for t in range(3):
+        assert np.array_equal(u[t], cold.u), t
+    # and a synchronous step after pipelined ones continues the same warm-start chain
+    nxt = s.step(states[3], dy, sp)
+    ref2 = _solver(B)
+    ref2.step(states[2], dy, sp)
+    assert np.array_equal(nxt.u, ref2.step(states[3], dy, sp).u)
