@@ -785,7 +785,9 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, boo
 #pragma unroll
     for (int q = 0; q < j; ++q) d -= A4[j][q] * A4[j][q];
     if (!(d > 0.0)) ok = false;
-    const double inv = 1.0 / sqrt(d);
+    double root_, inv;
+    fm::sqrt_rsqrt(d, root_, inv);  // straight-line 1 / sqrt(d): libdevice's division + square root carry slow paths
+    (void)root_;
     A4[j][j] = inv;
 #pragma unroll
     for (int i = j + 1; i < 4; ++i) {
@@ -1010,8 +1012,22 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
                                A[4 * r + 3] * Ph[12 + j];
 #pragma unroll
             for (int q = 0; q < 16; ++q) Ph[q] = T[q];
-            // Gamma_j <- A Gamma_j for the earlier knots of this chunk
-            for (int j = s * S + i0; j < col; ++j) {
+            // Gamma_j <- A Gamma_j for the earlier knots of this chunk, two columns per trip: the loads of a pair are
+            // issued ahead of its stores (the compiler cannot move a load above a store into the same array on its
+            // own), so the shared-memory latency is paid once per pair
+            int j = s * S + i0;
+            for (; j + 1 < col; j += 2) {
+              const double g0 = Gam[j], g1 = Gam[W + j], g2 = Gam[2 * W + j], g3 = Gam[3 * W + j];
+              const double h0 = Gam[j + 1], h1 = Gam[W + j + 1], h2 = Gam[2 * W + j + 1], h3 = Gam[3 * W + j + 1];
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                const double a = A[4 * r] * g0 + A[4 * r + 1] * g1 + A[4 * r + 2] * g2 + A[4 * r + 3] * g3;
+                const double b = A[4 * r] * h0 + A[4 * r + 1] * h1 + A[4 * r + 2] * h2 + A[4 * r + 3] * h3;
+                Gam[r * W + j] = a;
+                Gam[r * W + j + 1] = b;
+              }
+            }
+            if (j < col) {
               const double g0 = Gam[j], g1 = Gam[W + j], g2 = Gam[2 * W + j], g3 = Gam[3 * W + j];
 #pragma unroll
               for (int r = 0; r < 4; ++r)
