@@ -141,10 +141,10 @@ void BuildLayout(KernelCfg& k) {
   k.off_xc = k.off_gam;
   k.off_uc = k.off_xc + 4 * NS;
   k.off_xkc = k.off_uc + W;
-  // QP scratch: the condensed form's Z [4][W], tl [W], tinv [W]; the Riccati recursion only stages the feedback rows
+  // QP scratch: the condensed form's Z [4][W] and tinv [W]; the Riccati recursion only stages the feedback rows
   // of ONE segment here for its forward sweep (its value function lives in registers)
   const int n_ric = S * GAIN_STRIDE;
-  const int n_cond = k.condensed ? 6 * W : 0;
+  const int n_cond = k.condensed ? 5 * W : 0;
   k.off_aug = take(n_ric > n_cond ? n_ric : n_cond);
   k.off_dyn = take(12);
   // odd stride (in doubles) so that the same field of neighbouring instances falls into different banks

@@ -141,8 +141,8 @@ __device__ __forceinline__ double control_cost_partial(const Ctx& c, const Weigh
                                                        const double u_prev) {
   const KernelCfg& k = *c.cfg;
   double f = 0.0;
-  for (int s = c.gl; s < k.nseg; s += L) {
-    for (int i = 0; i < k.S; ++i) {
+    for (int s = c.gl; s < k.nseg; s += L) {
+        for (int i = 0; i < k.S; ++i) {
       const int col = s * k.S + i;
       const double uk = uu[col];
       if (w.w_r > 0.0) {
@@ -606,7 +606,7 @@ __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights& w, const
 // du = -L^-T D_T^-1 (z_g + Z sigma).  About 3 kflop instead of 15 kflop for the Riccati recursion, but the rows of U
 // are open-loop products of the segment transition matrices: accurate while the horizon is short (W dt of a fraction
 // of a second), useless on long unstable horizons (tests/prototypes/qp_riccati_proto.py) - the host picks.
-// Scratch (aliases the Riccati stage matrix): Z [4][W], tl [W], tinv [W].
+// Scratch (shared with the staging buffer of the Riccati recursion): Z [4][W], tinv [W].
 // ---------------------------------------------------------------------------------------------------------------------
 template <int L>
 __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, bool& tri_valid, const double x_cur[4],
@@ -620,14 +620,19 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, boo
   const double* ev = c.sm + k.off_e;
   const double* Gam = c.sm + k.off_gam;
   double* Z = c.sm + k.off_aug;  // [4][W]
-  double* tl = Z + 4 * W;        // sub-diagonal multipliers of the unit bidiagonal factor
-  double* tinv = tl + W;         // reciprocal pivots
+  double* tinv = Z + 4 * W;      // reciprocal pivots of T = L D L^T
+  // sub-diagonal multipliers of the unit bidiagonal factor: l_j = -w_r^2 / d_{j-1}, recomputed from the pivots where they
+  // are used (one multiply off the dependent chain) instead of being stored: W doubles less shared memory per instance,
+  // which is what lets a sixth warp fit on an SM at the default problem size
   const double wu2 = w.w_u * w.w_u, wr2 = w.w_r * w.w_r;
+  const double nwr2 = -wr2;
+#define CPMPC_TL(j) (nwr2 * tinv[(j) - 1])
   bool ok = true;
 
   // (1) factor T once per solve (lane L-1, while the other lanes build the rows of U)
   if (!tri_valid && c.gl == L - 1) {
     double dprev_inv = 0.0;
+    #pragma unroll 1
     for (int j = 0; j < W; ++j) {
       const double a = wu2 + wr2 * ((j + 1 < W) ? 2.0 : 1.0);
       double l = 0.0, d = a;
@@ -637,15 +642,16 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, boo
       }
       ok = ok && (d > 0.0);
       dprev_inv = fm::rcp(d);
-      tl[j] = l;
       tinv[j] = dprev_inv;
     }
   }
   tri_valid = true;
   // (2) rows of U: sensitivity of the terminal node to every control, through the later segments
+  #pragma unroll 1
   for (int col = c.gl; col < W; col += L) {
     const int s = col / S;
     double v0 = Gam[col], v1 = Gam[W + col], v2 = Gam[2 * W + col], v3 = Gam[3 * W + col];
+    #pragma unroll 1
     for (int t = s + 1; t < nseg; ++t) {
       const double* Ph = Phi + 16 * t;
       const double n0 = Ph[0] * v0 + Ph[1] * v1 + Ph[2] * v2 + Ph[3] * v3;
@@ -671,6 +677,7 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, boo
     m[i] = -d;
   }
   const double m00 = m[0], m01 = m[1], m02 = m[2], m03 = m[3];
+  #pragma unroll 1
   for (int s = 0; s < nseg; ++s) {
     const double* Ph = Phi + 16 * s;
     double n[4];
@@ -686,6 +693,7 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, boo
 
   // (3) forward substitution with the unit bidiagonal factor: rows 0..3 of Z and the gradient (in du[]), one
   // right-hand side per lane, the running value carried in a register
+  #pragma unroll 1
   for (int r = c.gl; r < 5; r += L) {
     double* row = (r < 4) ? (Z + r * W) : du;
     double prev = row[0];
@@ -694,7 +702,7 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, boo
     // every element pays a shared-memory round trip on top of the FMA.  Same operations in the same order.
     int j = 1;
     for (; j + 4 <= W; j += 4) {
-      const double t0 = tl[j], t1 = tl[j + 1], t2 = tl[j + 2], t3 = tl[j + 3];
+      const double t0 = CPMPC_TL(j), t1 = CPMPC_TL(j + 1), t2 = CPMPC_TL(j + 2), t3 = CPMPC_TL(j + 3);
       const double r0 = row[j], r1 = row[j + 1], r2 = row[j + 2], r3 = row[j + 3];
       const double p0 = fma(-t0, prev, r0);
       const double p1 = fma(-t1, p0, r1);
@@ -705,8 +713,9 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, boo
       row[j + 2] = p2;
       row[j + 3] = prev;
     }
+    #pragma unroll 1
     for (; j < W; ++j) {
-      prev = fma(-tl[j], prev, row[j]);
+      prev = fma(-CPMPC_TL(j), prev, row[j]);
       row[j] = prev;
     }
   }
@@ -721,6 +730,7 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, boo
   {
     // pair list: (0,0)(0,1)(0,2)(0,3)(1,1)(1,2)(1,3)(2,2)(2,3)(3,3)(0,4)(1,4)(2,4)(3,4)
     // every lane accumulates over its own columns q = gl, gl + L, ...; a group sum finishes each entry
+    #pragma unroll 1
     for (int q = c.gl; q < W; q += L) {
       const double ti = tinv[q];
       const double z0 = Z[q], z1 = Z[W + q], z2 = Z[2 * W + q], z3 = Z[3 * W + q], zg = du[q];
@@ -815,6 +825,7 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, boo
 
   // (6) du = -L^-T D^-1 (z_g + Z sigma); c_u . du = -(L^-1 g)^T D^-1 (z_g + Z sigma) needs no second pass over g
   double part = 0.0;
+  #pragma unroll 1
   for (int q = c.gl; q < W; q += L) {
     const double zg = du[q];
     const double wq = (zg + sig[0] * Z[q] + sig[1] * Z[W + q] + sig[2] * Z[2 * W + q] + sig[3] * Z[3 * W + q]) * tinv[q];
@@ -827,8 +838,9 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, boo
     double nxt = du[W - 1];
     du[W - 1] = -nxt;
     int j = W - 2;
+    #pragma unroll 1
     for (; j >= 3; j -= 4) {  // same batching as the forward substitution, descending
-      const double t0 = tl[j + 1], t1 = tl[j], t2 = tl[j - 1], t3 = tl[j - 2];
+      const double t0 = CPMPC_TL(j + 1), t1 = CPMPC_TL(j), t2 = CPMPC_TL(j - 1), t3 = CPMPC_TL(j - 2);
       const double d0 = du[j], d1 = du[j - 1], d2 = du[j - 2], d3 = du[j - 3];
       const double n0 = fma(-t0, nxt, d0);
       const double n1 = fma(-t1, n0, d1);
@@ -839,8 +851,9 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, boo
       du[j - 2] = -n2;
       du[j - 3] = -nxt;
     }
+    #pragma unroll 1
     for (; j >= 0; --j) {
-      nxt = fma(-tl[j + 1], nxt, du[j]);
+      nxt = fma(-CPMPC_TL(j + 1), nxt, du[j]);
       du[j] = -nxt;
     }
     dxs[0] = m00;
@@ -852,14 +865,17 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, boo
 
   // (7) node steps by forward propagation
   double xi[4] = {m00, m01, m02, m03};
+  #pragma unroll 1
   for (int s = 0; s < nseg; ++s) {
     const double* Ph = Phi + 16 * s;
+    #pragma unroll 1
     for (int a = c.gl; a < 4; a += L) {
       double n0 = Ph[4 * a] * xi[0] + Ph[4 * a + 1] * xi[1] + ev[4 * s + a];
       double n1 = Ph[4 * a + 2] * xi[2] + Ph[4 * a + 3] * xi[3];
       const double* ga = Gam + a * W + s * S;
       const double* vv = du + s * S;
       int j = 0;
+      #pragma unroll 1
       for (; j + 1 < S; j += 2) {
         n0 = fma(ga[j], vv[j], n0);
         n1 = fma(ga[j + 1], vv[j + 1], n1);
@@ -872,6 +888,7 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, boo
     for (int a = 0; a < 4; ++a) xi[a] = dxs[4 * (s + 1) + a];
   }
   return true;
+#undef CPMPC_TL
 }
 
 struct SolveResult {
@@ -953,6 +970,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
 
   // gradient of the control costs at the current controls into du[] (the QP routines consume and overwrite it)
   auto fill_gradient = [&]() {
+    #pragma unroll 1
     for (int col = c.gl; col < W; col += L) {
       double g = 0.0;
       const double uk = u[col];
@@ -968,6 +986,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
     CPMPC_GSYNC();
   };
 
+  #pragma unroll 1
   for (int iter = 0; iter < k.max_iter; ++iter) {
     if (!__any_sync(0xffffffffu, active)) break;
 
@@ -1052,6 +1071,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
       if (cps > 1) {
         // stitch the chunks of a segment: Phi_s = Phi_{cps-1} ... Phi_0, Gamma_j <- (Phi_{cps-1} ... Phi_{cc+1}) Gamma_j
         CPMPC_GSYNC();
+        #pragma unroll 1
         for (int base = 0; base < k.nchunk; base += L) {  // uniform trip count: the loop body synchronises
           const int id = base + c.gl;
           const int s = id / cps, cc = id - s * cps;
@@ -1061,6 +1081,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
             const double* last = PhiC + 16 * (s * cps + cps - 1);
 #pragma unroll
             for (int q = 0; q < 16; ++q) Sx[q] = last[q];
+            #pragma unroll 1
             for (int m = cps - 2; m > cc; --m) {
               const double* Pm = PhiC + 16 * (s * cps + m);
               double T[16];
@@ -1096,6 +1117,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
           }
         }
         CPMPC_GSYNC();
+        #pragma unroll 1
         for (int col = c.gl; col < W; col += L) {
           const int s = col / S, i = col - s * S;
           const int cc = ((i + 1) * cps - 1) / S;
@@ -1162,14 +1184,19 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
         // debug view: the blocks of this linearisation and the QP step, then stop (the candidates would overwrite Gam)
         CPMPC_GSYNC();
         double* o = dbg;
+        #pragma unroll 1
         for (int q = c.gl; q < 16 * nseg; q += L) o[q] = Phi[q];
         o += 16 * nseg;
+        #pragma unroll 1
         for (int q = c.gl; q < 4 * W; q += L) o[q] = Gam[q];
         o += 4 * W;
+        #pragma unroll 1
         for (int q = c.gl; q < 4 * nseg; q += L) o[q] = ev[q];
         o += 4 * nseg;
+        #pragma unroll 1
         for (int q = c.gl; q < 4 * NS; q += L) o[q] = dxs[q];
         o += 4 * NS;
+        #pragma unroll 1
         for (int q = c.gl; q < W; q += L) o[q] = du[q];
         o += W;
         if (c.gl == 0) {
@@ -1188,12 +1215,14 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
         // quadratic form dx^T G dx and the directional derivatives (nonlinear.cc:457-502)
         double quad = 0.0;
         const double wu2 = w.w_u * w.w_u, wr2 = w.w_r * w.w_r;
+        #pragma unroll 1
         for (int col = c.gl; col < W; col += L) {
           const double a = wu2 + lambda + wr2 * ((col + 1 < W) ? 2.0 : 1.0);
           const double v = du[col];
           quad += a * v * v;
           if (col + 1 < W) quad -= 2.0 * wr2 * v * du[col + 1];
         }
+        #pragma unroll 1
         for (int q = c.gl; q < NS; q += L) {
           const double* m = dxs + 4 * q;
           quad += lambda * (m[0] * m[0] + m[1] * m[1] + m[2] * m[2] + m[3] * m[3]);
@@ -1216,6 +1245,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
           }
           // every other equality row satisfies A_i.dx = -b_i by construction of dx
           double l1_other = 0.0;
+          #pragma unroll 1
           for (int q = 0; q < 4 * nseg; ++q) l1_other += fabs(ev[q]);
 #pragma unroll
           for (int i = 0; i < 4; ++i) l1_other += fabs(dxs[i]);
@@ -1258,6 +1288,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
     step_f = step_eq = 0.0;
     n_steps = 0;
     double* lrow = (iter_log != nullptr && active) ? iter_log + (size_t)iter * CPMPC_ITERLOG_STRIDE : nullptr;
+    #pragma unroll 1
     for (int ls = 0; ls <= k.max_ls; ++ls) {
       if (__all_sync(0xffffffffu, ls_done)) break;
       if (!ls_done && ls > 0) {
@@ -1337,9 +1368,12 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
     if (active) {
       bool exit_now = false;
       if (step_result == SR_SUCCESS) {
+        #pragma unroll 1
         for (int q = c.gl; q < 4 * NS; q += L) xs[q] = xc[q];
+        #pragma unroll 1
         for (int col = c.gl; col < W; col += L) u[col] = uc[col];
         if (cps > 1)
+          #pragma unroll 1
           for (int q = c.gl; q < 4 * k.nchunk; q += L) xk[q] = xkc[q];
         CPMPC_GSYNC();
         lambda = fmax(lambda * ((opt_state == OS_RESTORE_LM) ? k.lam_dec_restore : k.lam_dec_success), k.lam_min);
@@ -1430,6 +1464,7 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
 #pragma unroll
   for (int i = 0; i < N_PHASES; ++i) wph.ph[i] = 0;
   wph.ph[N_PHASES] = t_begin;
+  #pragma unroll 1
   for (;;) {
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(io.queue, (unsigned long long)G);
@@ -1487,6 +1522,7 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
     long long& sum_ls = kc.sum_ls;
     long long& sum_bad = kc.sum_bad;
     solves = sum_iter = sum_ls = sum_bad = 0;
+    #pragma unroll 1
     for (long long step = 0; step < io.n_steps; ++step) {
       // ---- BuildProblem + initial guess (optimization.cc:44-71) ---------------------------------------------------
       double& u_prev = kc.u_prev;
@@ -1495,6 +1531,7 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
         double* prev = io.prev + inst * N;
         const bool warm = io.has_prev[inst] != 0;
         if (warm) u_prev = prev[4 * NS];  // last step's applied control (optimization.cc:289-291)
+        #pragma unroll 1
         for (int q = c.gl; q < W; q += L) {
           u[q] = warm ? prev[4 * NS + ((q + 1 < W) ? q + 1 : q)] : io.u_guess[q];
         }
@@ -1508,9 +1545,11 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
           double* xk = c.sm + cfg.off_xk;
 #pragma unroll
           for (int i = 0; i < 4; ++i) xs[i] = x[i];
+          #pragma unroll 1
           for (int s = 1; s < NS; ++s) {
             int cc = 1;
             int nb = (cfg.cps > 1) ? (S / cfg.cps) : S;
+            #pragma unroll 1
             for (int i = 0; i < S; ++i) {
               if (i == nb) {
                 double* dst = xk + 4 * ((s - 1) * cfg.cps + cc);
@@ -1549,7 +1588,9 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
         const bool keep = res.termination != TS_REJECTED && io.dbg == nullptr;
         double* prev = io.prev + inst * N;
         if (keep)
+          #pragma unroll 1
           for (int q = c.gl; q < 4 * NS; q += L) prev[q] = xs[q];
+        #pragma unroll 1
         for (int q = c.gl; q < W; q += L) {
           if (keep) prev[4 * NS + q] = u[q];
           if (io.u_out != nullptr) io.u_out[inst * W + q] = u[q];
@@ -1562,6 +1603,7 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
             load_dyn_const(Pl, c.sm + cfg.off_dyn);
             double x[4] = {x_cur[0], x_cur[1], x_cur[2], x_cur[3]};
             double* po = io.pred_out + (size_t)inst * W * 4;
+            #pragma unroll 1
             for (int q = 0; q < W; ++q) {
               rk4_step<false>(Pl, x, u[q], cfg.dt);
               x[1] = mod_pi(x[1]);
