@@ -870,6 +870,7 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights<PL::NX>
   // (1) factor T once per solve (lane L-1, while the other lanes build the rows of U)
   if (!tri_valid && c.gl == L - 1) {
     double dprev_inv = 0.0;
+    #pragma unroll 1
     for (int j = 0; j < W; ++j) {
       const double a = wu2 + wr2 * ((j + 1 < W) ? 2.0 : 1.0);
       double l = 0.0, d = a;
@@ -885,11 +886,13 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights<PL::NX>
   }
   tri_valid = true;
   // (2) rows of U: sensitivity of the terminal node to every control, through the later segments
+  #pragma unroll 1
   for (int col = c.gl; col < W; col += L) {
     const int s = col / S;
     double v[NX];
 #pragma unroll
     for (int a = 0; a < NX; ++a) v[a] = Gam[a * W + col];
+    #pragma unroll 1
     for (int t = s + 1; t < nseg; ++t) {
       const double* Ph = Phi + NX * NX * t;
       double n[NX];
@@ -915,6 +918,7 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights<PL::NX>
     m[i] = -d;
     m0[i] = -d;
   }
+  #pragma unroll 1
   for (int s = 0; s < nseg; ++s) {
     const double* Ph = Phi + NX * NX * s;
     double n[NX];
@@ -934,9 +938,11 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights<PL::NX>
 
   // (3) forward substitution with the unit bidiagonal factor: the NX rows of Z and the gradient (in du[]), one
   // right-hand side per lane, the running value carried in a register
+  #pragma unroll 1
   for (int r = c.gl; r < NX + 1; r += L) {
     double* row = (r < NX) ? (Z + r * W) : du;
     double prev = row[0];
+    #pragma unroll 1
     for (int j = 1; j < W; ++j) {
       prev = fma(-tl[j], prev, row[j]);
       row[j] = prev;
@@ -949,6 +955,7 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights<PL::NX>
   double gm[NP + NX];
 #pragma unroll
   for (int e = 0; e < NP + NX; ++e) gm[e] = 0.0;
+  #pragma unroll 1
   for (int q = c.gl; q < W; q += L) {
     const double ti = tinv[q];
     const double zg = du[q];
@@ -1053,6 +1060,7 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights<PL::NX>
 
   // (6) du = -L^-T D^-1 (z_g + Z sigma); c_u . du = -(L^-1 g)^T D^-1 (z_g + Z sigma)
   double part = 0.0;
+  #pragma unroll 1
   for (int q = c.gl; q < W; q += L) {
     const double zg = du[q];
     double acc = zg;
@@ -1067,6 +1075,7 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights<PL::NX>
   if (c.gl == 0) {
     double nxt = du[W - 1];
     du[W - 1] = -nxt;
+    #pragma unroll 1
     for (int j = W - 2; j >= 0; --j) {
       nxt = fma(-tl[j + 1], nxt, du[j]);
       du[j] = -nxt;
@@ -1080,8 +1089,10 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights<PL::NX>
   double xi[NX];
 #pragma unroll
   for (int i = 0; i < NX; ++i) xi[i] = m0[i];
+  #pragma unroll 1
   for (int s = 0; s < nseg; ++s) {
     const double* Ph = Phi + NX * NX * s;
+    #pragma unroll 1
     for (int a = c.gl; a < NX; a += L) {
       double n0 = ev[NX * s + a];
 #pragma unroll
@@ -1089,6 +1100,7 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights<PL::NX>
       const double* ga = Gam + a * W + s * S;
       const double* vv = du + s * S;
       double n1 = 0.0;
+      #pragma unroll 1
       for (int j = 0; j < S; ++j) n1 = fma(ga[j], vv[j], n1);
       dxs[NX * (s + 1) + a] = n0 + n1;
     }
@@ -1154,6 +1166,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
 
   // gradient of the control costs at the current controls into du[] (the QP routines consume and overwrite it)
   auto fill_gradient = [&]() {
+    #pragma unroll 1
     for (int col = c.gl; col < W; col += L) {
       double g = 0.0;
       const double uk = u[col];
@@ -1169,6 +1182,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
     GP_GSYNC();
   };
 
+  #pragma unroll 1
   for (int iter = 0; iter < k.max_iter; ++iter) {
     if (!__any_sync(0xffffffffu, active)) break;
     double& f0 = cold.f0;
@@ -1291,12 +1305,14 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
         // dx^T G dx and the directional derivatives (nonlinear.cc:457-502)
         double quad = 0.0;
         const double wu2 = w.w_u * w.w_u, wr2 = w.w_r * w.w_r;
+        #pragma unroll 1
         for (int col = c.gl; col < W; col += L) {
           const double a = wu2 + lambda + wr2 * ((col + 1 < W) ? 2.0 : 1.0);
           const double v = du[col];
           quad += a * v * v;
           if (col + 1 < W) quad -= 2.0 * wr2 * v * du[col + 1];
         }
+        #pragma unroll 1
         for (int q = c.gl; q < NS; q += L) {
           const double* m = dxs + NX * q;
           double ss = 0.0;
@@ -1320,6 +1336,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
             }
           }
           double l1_other = 0.0;
+          #pragma unroll 1
           for (int q = 0; q < NX * nseg; ++q) l1_other += fabs(ev[q]);
 #pragma unroll
           for (int i = 0; i < NX; ++i) l1_other += fabs(dxs[i]);
@@ -1359,6 +1376,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
     step_f = step_eq = 0.0;
     n_steps = 0;
     double* lrow = (iter_log != nullptr && active) ? iter_log + (size_t)iter * CPMPC_ITERLOG_STRIDE : nullptr;
+    #pragma unroll 1
     for (int ls = 0; ls <= k.max_ls; ++ls) {
       if (__all_sync(0xffffffffu, ls_done)) break;
       if (!ls_done && ls > 0) {
@@ -1437,7 +1455,9 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
     if (active) {
       bool exit_now = false;
       if (step_result == SR_SUCCESS) {
+        #pragma unroll 1
         for (int q = c.gl; q < NX * NS; q += L) xs[q] = xc[q];
+        #pragma unroll 1
         for (int col = c.gl; col < W; col += L) u[col] = uc[col];
         GP_GSYNC();
         lambda = fmax(lambda * ((opt_state == OS_RESTORE_LM) ? k.lam_dec_restore : k.lam_dec_success), k.lam_min);
@@ -1514,6 +1534,7 @@ __global__ void __launch_bounds__(256, 1) plant_solve_kernel(const GpCfg cfg, co
   double* xs = c.sm + cfg.off_xs;
   double* u = c.sm + cfg.off_u;
 
+  #pragma unroll 1
   for (;;) {
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(io.queue, (unsigned long long)G);
@@ -1570,6 +1591,7 @@ __global__ void __launch_bounds__(256, 1) plant_solve_kernel(const GpCfg cfg, co
       double* prev = io.prev + inst * N;
       const bool warm = io.has_prev[inst] != 0;
       if (warm) u_prev = prev[NX * NS];
+      #pragma unroll 1
       for (int q = c.gl; q < W; q += L) u[q] = warm ? prev[NX * NS + ((q + 1 < W) ? q + 1 : q)] : io.u_guess[q];
       GP_GSYNC();
       if (c.gl == 0) {
@@ -1582,7 +1604,9 @@ __global__ void __launch_bounds__(256, 1) plant_solve_kernel(const GpCfg cfg, co
           x[i] = x_cur[i];
           xs[i] = x[i];
         }
+        #pragma unroll 1
         for (int s = 1; s < NS; ++s) {
+          #pragma unroll 1
           for (int i = 0; i < S; ++i) {
             rk4_step<PL>(Pl, x, u[(s - 1) * S + i], cfg.dt);
 #pragma unroll
@@ -1604,7 +1628,9 @@ __global__ void __launch_bounds__(256, 1) plant_solve_kernel(const GpCfg cfg, co
 
     if (have) {
       double* prev = io.prev + inst * N;
+      #pragma unroll 1
       for (int q = c.gl; q < NX * NS; q += L) prev[q] = xs[q];
+      #pragma unroll 1
       for (int q = c.gl; q < W; q += L) {
         prev[NX * NS + q] = u[q];
         if (io.u_out != nullptr) io.u_out[inst * W + q] = u[q];
@@ -1619,6 +1645,7 @@ __global__ void __launch_bounds__(256, 1) plant_solve_kernel(const GpCfg cfg, co
 #pragma unroll
           for (int i = 0; i < NX; ++i) x[i] = x_cur[i];
           double* po = io.pred_out + (size_t)inst * W * NX;
+          #pragma unroll 1
           for (int q = 0; q < W; ++q) {
             rk4_step<PL>(Pl, x, u[q], cfg.dt);
 #pragma unroll
