@@ -33,37 +33,53 @@ namespace fm {
 // immediates, so a literal costs two UMOVs (and a uniform-datapath latency) in front of every DFMA that uses it,
 // whereas a constant-bank table is fetched into uniform registers two doubles per LDCU.128.
 #define CPMPC_FM_CONSTS(X) \
-  X(two_over_pi, 0.63661977236758138) \
-  X(magic, 6755399441055744.0) \
-  X(pio2_1, 1.5707963267948966) \
-  X(pio2_2, 6.123233995736766e-17) \
-  X(pio2_3, -1.4973849048591698e-33) \
-  X(s6, 1.58969099521155010221e-10) \
+  X(pio2_2, 0x1.5110b4611a626p-22) \
+  X(pio2_3, 0x1.98a2e03707345p-77) \
   X(s5, -2.50507602534068634195e-08) \
   X(s4, 2.75573137070700676789e-06) \
   X(s3, -1.98412698298579493134e-04) \
   X(s2, 8.33333333332248946124e-03) \
   X(s1, -1.66666666666666324348e-01) \
-  X(c6, -1.13596475577881948265e-11) \
   X(c5, 2.08757232129817482790e-09) \
   X(c4, -2.75573143513906633035e-07) \
   X(c3, 2.48015872894767294178e-05) \
   X(c2, -1.38888888888741095749e-03) \
   X(c1, 4.16666666666666019037e-02) \
-  X(log2e, 1.4426950408889634) \
-  X(ln2_hi, 6.93147180369123816490e-01) \
-  X(ln2_lo, 1.90821492927058770002e-10) \
-  X(e12, 1.0 / 479001600.0) \
-  X(e10, 1.0 / 3628800.0) \
+  X(ln2_lo, -0x1.05c610ca86c39p-29) \
   X(e8, 1.0 / 40320.0) \
   X(e6, 1.0 / 720.0) \
   X(e4, 1.0 / 24.0) \
-  X(e13, 1.0 / 6227020800.0) \
-  X(e11, 1.0 / 39916800.0) \
   X(e9, 1.0 / 362880.0) \
   X(e7, 1.0 / 5040.0) \
   X(e5, 1.0 / 120.0) \
   X(e3, 1.0 / 6.0)
+// Five FMAs of the chains below take TWO constants (the start of each Horner chain, fma(z, c_top, c_next), and the
+// 1.5 * 2^52 rounding trick), and an FP64 instruction takes at most ONE operand from the constant bank or a uniform
+// register: the other had to sit in an ordinary register, which ptxas either hoisted out of the caller's stage loop
+// (ten registers held across the whole rollout) or, under register pressure, re-loaded with LDC.64 in every dynamics
+// evaluation right in front of its use, on the critical path (the linearisation loop; and the merit loop flipped
+// between the two with unrelated changes elsewhere in the solver).  A double whose low 32 bits are zero is encodable
+// as an IMMEDIATE operand instead.  The magic number is such a value; the four top polynomial coefficients are rounded
+// to 21 significant bits here: each multiplies the highest power of a reduced argument, so the change is below 3e-18
+// relative to the result (0.03 ulp; tests/test_fastmath.py holds the functions to the same bounds as before).
+// The same encoding serves wherever 21 bits are enough or the remainder can go into the next term:
+//   * 2/pi and log2(e) only pick the integer k of the range reduction; a relative error of 3e-7 moves the reduced
+//     argument at most 1e-4 beyond its nominal interval, where the polynomials are as accurate as inside;
+//   * pi/2 = kPio2Hi + pio2_2 + pio2_3 and ln 2 = kLn2Hi + ln2_lo are split so that the leading part is an immediate
+//     (k * leading part is exact in the FMA either way; the sums carry 127 and 74 bits);
+//   * 1/10! and 1/11! multiply r^10 and r^11 with |r| <= ln2 / 2 (2e-18 relative to exp(r)).
+constexpr double kTwoOverPi = 0x1.45f3p-1;          // 2 / pi to 21 bits
+constexpr double kPio2Hi = 0x1.921fbp+0;            // pi / 2 to 21 bits
+constexpr double kLog2e = 0x1.71547p+0;             // log2(e) to 21 bits
+constexpr double kLn2Hi = 0x1.62e43p-1;             // ln 2 to 21 bits
+constexpr double kE10 = 0x1.27e5p-22;               // 1 / 10! to 21 bits
+constexpr double kE11 = 0x1.ae645p-26;              // 1 / 11! to 21 bits
+constexpr double kMagic = 0x1.8p+52;                // 1.5 * 2^52
+constexpr double kS6 = 0x1.5d93ap-33;               // 1.58969099521155010221e-10 (fdlibm S6) to 21 bits
+constexpr double kC6 = -0x1.8fae9p-37;              // -1.13596475577881948265e-11 (fdlibm C6) to 21 bits
+constexpr double kE12 = 0x1.1eed8p-29;              // 1 / 12! to 21 bits
+constexpr double kE13 = 0x1.61246p-33;              // 1 / 13! to 21 bits
+
 struct FmConsts {
 #define CPMPC_X(name, value) double name;
   CPMPC_FM_CONSTS(CPMPC_X)
@@ -126,11 +142,24 @@ CPMPC_HD void sqrt_rsqrt(double x, double& root, double& inv_root) {
   inv_root = h + h;
 }
 
+// x with its sign bit XORed with `sbit` (0 or 0x80000000).
+CPMPC_HD double flip_sign(double x, uint32_t sbit) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(__double2hiint(x) ^ (int)sbit, __double2loint(x));
+#else
+  uint64_t b;
+  memcpy(&b, &x, sizeof(b));
+  b ^= (uint64_t)sbit << 32;
+  memcpy(&x, &b, sizeof(b));
+  return x;
+#endif
+}
+
 // sin and cos for |x| < 2^20 (the pole angle stays within a few turns between two mod_pi wraps).
 CPMPC_HD void sincos_bf(double x, double& s_out, double& c_out) {
   // k = round(x * 2/pi) with the 1.5 * 2^52 trick; its low bits give the quadrant
-  const double magic = CPMPC_K(magic);
-  const double t = CPMPC_FMA(x, CPMPC_K(two_over_pi), magic);
+  const double magic = kMagic;
+  const double t = CPMPC_FMA(x, kTwoOverPi, magic);
   const double kd = t - magic;
   int64_t tb;
 #if defined(__CUDA_ARCH__)
@@ -140,18 +169,18 @@ CPMPC_HD void sincos_bf(double x, double& s_out, double& c_out) {
 #endif
   const int q = (int)(tb & 3);
   // Cody-Waite with a three-part pi/2 (the FMAs keep the products exact)
-  double r = CPMPC_FMA(-kd, CPMPC_K(pio2_1), x);
+  double r = CPMPC_FMA(-kd, kPio2Hi, x);
   r = CPMPC_FMA(-kd, CPMPC_K(pio2_2), r);
   r = CPMPC_FMA(-kd, CPMPC_K(pio2_3), r);
   const double z = r * r;
   // fdlibm kernel polynomials on |r| <= pi/4
-  double ps = CPMPC_FMA(z, CPMPC_K(s6), CPMPC_K(s5));
+  double ps = CPMPC_FMA(z, kS6, CPMPC_K(s5));
   ps = CPMPC_FMA(z, ps, CPMPC_K(s4));
   ps = CPMPC_FMA(z, ps, CPMPC_K(s3));
   ps = CPMPC_FMA(z, ps, CPMPC_K(s2));
   ps = CPMPC_FMA(z, ps, CPMPC_K(s1));
   const double sn = CPMPC_FMA(z * r, ps, r);
-  double pc = CPMPC_FMA(z, CPMPC_K(c6), CPMPC_K(c5));
+  double pc = CPMPC_FMA(z, kC6, CPMPC_K(c5));
   pc = CPMPC_FMA(z, pc, CPMPC_K(c4));
   pc = CPMPC_FMA(z, pc, CPMPC_K(c3));
   pc = CPMPC_FMA(z, pc, CPMPC_K(c2));
@@ -161,16 +190,18 @@ CPMPC_HD void sincos_bf(double x, double& s_out, double& c_out) {
   const bool swap = (q & 1) != 0;
   const double sv = swap ? cs : sn;
   const double cv = swap ? sn : cs;
-  s_out = (q & 2) ? -sv : sv;
-  c_out = ((q + 1) & 2) ? -cv : cv;
+  // quadrant signs by flipping the sign bit (one integer instruction on the high word each, instead of an FP64
+  // negation and a two-register select): bit 1 of q for the sine, bit 1 of q + 1 for the cosine
+  s_out = flip_sign(sv, (uint32_t)(q & 2) << 30);
+  c_out = flip_sign(cv, (uint32_t)((q + 1) & 2) << 30);
 }
 
 // tanh(x) with ABSOLUTE error ~2e-16 (enough here: it multiplies the friction force inside a sum of O(1) forces).
 CPMPC_HD double tanh_bf(double x) {
   const double ax = fmin(fabs(x), 20.0);
   const double y = -2.0 * ax;  // em = exp(y) in (4e-18, 1]
-  const double magic = CPMPC_K(magic);
-  const double t = CPMPC_FMA(y, CPMPC_K(log2e), magic);
+  const double magic = kMagic;
+  const double t = CPMPC_FMA(y, kLog2e, magic);
   const double nd = t - magic;
   int64_t tb;
 #if defined(__CUDA_ARCH__)
@@ -179,17 +210,17 @@ CPMPC_HD double tanh_bf(double x) {
   memcpy(&tb, &t, sizeof(tb));
 #endif
   const int n = (int)(int32_t)(tb & 0xffffffff);  // in [-58, 0]
-  double r = CPMPC_FMA(-nd, CPMPC_K(ln2_hi), y);
+  double r = CPMPC_FMA(-nd, kLn2Hi, y);
   r = CPMPC_FMA(-nd, CPMPC_K(ln2_lo), r);
   // exp(r), |r| <= ln2/2: Taylor to r^13, even/odd split to halve the dependent depth
   const double r2 = r * r;
-  double pe = CPMPC_FMA(r2, CPMPC_K(e12), CPMPC_K(e10));  // r^12, r^10
+  double pe = CPMPC_FMA(r2, kE12, kE10);  // r^12, r^10
   pe = CPMPC_FMA(r2, pe, CPMPC_K(e8));
   pe = CPMPC_FMA(r2, pe, CPMPC_K(e6));
   pe = CPMPC_FMA(r2, pe, CPMPC_K(e4));
   pe = CPMPC_FMA(r2, pe, 0.5);
   pe = CPMPC_FMA(r2, pe, 1.0);
-  double po = CPMPC_FMA(r2, CPMPC_K(e13), CPMPC_K(e11));  // r^13, r^11
+  double po = CPMPC_FMA(r2, kE13, kE11);  // r^13, r^11
   po = CPMPC_FMA(r2, po, CPMPC_K(e9));
   po = CPMPC_FMA(r2, po, CPMPC_K(e7));
   po = CPMPC_FMA(r2, po, CPMPC_K(e5));
