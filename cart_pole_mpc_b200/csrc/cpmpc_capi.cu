@@ -146,7 +146,7 @@ void BuildLayout(KernelCfg& k) {
   const int n_ric = S * GAIN_STRIDE;
   const int n_cond = k.condensed ? 5 * W : 0;
   k.off_aug = take(n_ric > n_cond ? n_ric : n_cond);
-  k.off_dyn = take(12);
+  k.off_dyn = take(DYN_CONST_DOUBLES);
   // odd stride (in doubles) so that the same field of neighbouring instances falls into different banks
   k.stride = off | 1;
   k.kk_stride = W * GAIN_STRIDE;

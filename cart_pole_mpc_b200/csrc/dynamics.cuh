@@ -6,42 +6,58 @@
 //   mod_pi                    optimization/integration.hpp:65-73                -> mod_pi
 //
 // Differences from the generated reference code that matter for speed and are exact or ulp-level:
-//   * every sub-expression that depends only on SingleCartPoleParams (1/l, M/l^2, -c_d/6, -(M mu_b) g, 1/v_mu ...)
-//     is hoisted into DynConst once per instance: 3 of the 6 divisions per evaluation disappear;
+//   * every product that depends only on SingleCartPoleParams (1/l, (m_1 + m_b)/(m_1 l^2), -c_d/2, -(M mu_b) g, 1/v_mu,
+//     -l g m_1 ...) is hoisted into DynConst once per instance, and the factor m_1 common to the numerators and the
+//     mass-matrix determinant is cancelled: one reciprocal per evaluation (the generated code has six divisions);
 //   * the state Jacobian of the dynamics has two constant rows ([0 0 1 0], [0 0 0 1]); only rows 2-3 (8 numbers) and
-//     the two non-zero entries of the control Jacobian are produced, and the RK4 chain rule uses that structure
-//     (32 instead of 64 FMAs per stage product);
+//     the two non-zero entries of the control Jacobian are produced, from the closed-form derivatives of the drag
+//     terms, and the RK4 chain rule uses that structure (32 instead of 64 FMAs per stage product);
 //   * sin/cos, tanh, sqrt and the reciprocals come from fastmath.cuh (branch-free, ~1 ulp) so that one evaluation is
-//     a single basic block whose four long dependent chains overlap;
-//   * 1/(det*det) is computed as (1/det)^2 (1 ulp).
+//     a single basic block whose four long dependent chains overlap.
+// The file also compiles for the host (tests/native/dynamics_check.cc).
 #pragma once
+#if defined(__CUDACC__)
 #include <cuda_runtime.h>
+#define CPMPC_DEV __device__ __forceinline__
+#else
+// host build of the same code (tests/native/dynamics_check.cc compares it with the oracle's restatement of the
+// generated dynamics, which is bit-equal to the reference)
+#include <cmath>
+#define CPMPC_DEV inline
+#endif
 
 #include "fastmath.cuh"
 
 namespace cpmpc {
 
+constexpr int DYN_CONST_DOUBLES = 16;
+
+// Everything of an evaluation that depends on SingleCartPoleParams only, computed once per instance.
 struct DynConst {
   double m1;         // pole mass
   double m_total;    // m_1 + m_b
   double len;        // l_1
   double inv_len;    // 1 / l_1
-  double len2;       // 2 l_1
-  double m_over_l2;  // (m_1 + m_b) / l_1^2
-  double drag_k;     // -c_d / 6
+  double kappa;      // (m_1 + m_b) / (m_1 l_1^2)
+  double k30;        // 3 * (-c_d / 6): drag force = k30 * |v_mass| * v_mass
+  double k30len;     // k30 * l_1
+  double k30len2;    // k30 * l_1^2
   double fric_k;     // -(m_total mu_b) g
   double inv_v_cut;  // 1 / max(v_mu_b, 1e-6)
+  double fric_kv;    // fric_k * inv_v_cut
   double k_s;        // bumper spring constant
   double x_s;        // bumper position
-  double grav;       // g
+  double nlgm;       // -l_1 g m_1
+  double m1len;      // m_1 l_1
+  double m1x2;       // 2 m_1
 };
 
-__device__ __forceinline__ DynConst make_dyn_const(const double* __restrict__ p) {
+CPMPC_DEV DynConst make_dyn_const(const double* __restrict__ p) {
   DynConst c;
   const double m_b = p[0];
   c.m1 = p[1];
   c.len = p[2];
-  c.grav = p[3];
+  const double grav = p[3];
   const double mu_b = p[4];
   const double v_mu = p[5];
   const double c_d = p[6];
@@ -49,47 +65,67 @@ __device__ __forceinline__ DynConst make_dyn_const(const double* __restrict__ p)
   c.k_s = p[8];
   c.m_total = c.m1 + m_b;
   c.inv_len = 1.0 / c.len;
-  c.len2 = c.len * 2.0;
-  c.m_over_l2 = c.m_total * (1.0 / (c.len * c.len));
-  c.drag_k = (-0.16666666666666666) * c_d;
-  c.fric_k = (c.m_total * mu_b) * -c.grav;
+  c.kappa = c.m_total / (c.m1 * (c.len * c.len));
+  c.k30 = -0.5 * c_d;
+  c.k30len = c.k30 * c.len;
+  c.k30len2 = c.k30len * c.len;
+  c.fric_k = (c.m_total * mu_b) * -grav;
   c.inv_v_cut = 1.0 / ((1e-06 < v_mu) ? v_mu : 1e-06);
+  c.fric_kv = c.fric_k * c.inv_v_cut;
+  c.nlgm = -(c.len * (grav * c.m1));
+  c.m1len = c.m1 * c.len;
+  c.m1x2 = c.m1 + c.m1;
   return c;
 }
 
-// DynConst parked in / fetched from shared memory (12 doubles).
-__device__ __forceinline__ void store_dyn_const(double* dst, const DynConst& c) {
+// DynConst parked in / fetched from shared memory (DYN_CONST_DOUBLES doubles).
+CPMPC_DEV void store_dyn_const(double* dst, const DynConst& c) {
   dst[0] = c.m1;
   dst[1] = c.m_total;
   dst[2] = c.len;
   dst[3] = c.inv_len;
-  dst[4] = c.len2;
-  dst[5] = c.m_over_l2;
-  dst[6] = c.drag_k;
-  dst[7] = c.fric_k;
-  dst[8] = c.inv_v_cut;
-  dst[9] = c.k_s;
-  dst[10] = c.x_s;
-  dst[11] = c.grav;
+  dst[4] = c.kappa;
+  dst[5] = c.k30;
+  dst[6] = c.k30len;
+  dst[7] = c.k30len2;
+  dst[8] = c.fric_k;
+  dst[9] = c.inv_v_cut;
+  dst[10] = c.fric_kv;
+  dst[11] = c.k_s;
+  dst[12] = c.x_s;
+  dst[13] = c.nlgm;
+  dst[14] = c.m1len;
+  dst[15] = c.m1x2;
 }
-__device__ __forceinline__ void load_dyn_const(DynConst& c, const double* src) {
+CPMPC_DEV void load_dyn_const(DynConst& c, const double* src) {
   c.m1 = src[0];
   c.m_total = src[1];
   c.len = src[2];
   c.inv_len = src[3];
-  c.len2 = src[4];
-  c.m_over_l2 = src[5];
-  c.drag_k = src[6];
-  c.fric_k = src[7];
-  c.inv_v_cut = src[8];
-  c.k_s = src[9];
-  c.x_s = src[10];
-  c.grav = src[11];
+  c.kappa = src[4];
+  c.k30 = src[5];
+  c.k30len = src[6];
+  c.k30len2 = src[7];
+  c.fric_k = src[8];
+  c.inv_v_cut = src[9];
+  c.fric_kv = src[10];
+  c.k_s = src[11];
+  c.x_s = src[12];
+  c.nlgm = src[13];
+  c.m1len = src[14];
+  c.m1x2 = src[15];
+}
+
+// The constants of a harmless plant (unit masses and length, no friction, drag or bumpers) for lane groups that carry
+// no instance but still walk through the phases with their warp.
+CPMPC_DEV DynConst dummy_dyn_const() {
+  const double p[9] = {1.0, 1.0, 1.0, 9.81, 0.0, 1.0, 0.0, 1.0, 0.0};
+  return make_dyn_const(p);
 }
 
 // Map an angle to (-pi, pi].  fmod(a, 2pi) == a exactly whenever |a| < 2pi, which skips CUDA's software fmod on
 // the overwhelmingly common path.
-__device__ __forceinline__ double mod_pi(double a) {
+CPMPC_DEV double mod_pi(double a) {
   constexpr double pi = 3.141592653589793;
   constexpr double two_pi = 6.283185307179586;
   if (!(fabs(a) < two_pi)) a = fmod(a, two_pi);
@@ -98,24 +134,36 @@ __device__ __forceinline__ double mod_pi(double a) {
   return a;
 }
 
+// The equations of motion in the form evaluated here (b_x, th, v = b_x', w = th'; s = sin th, c = cos th):
+//     D      = m_total - m_1 s^2                                  (mass-matrix determinant over m_1 l^2)
+//     v_x    = v - l w s,   proj = l w c^2 - v_x s,   |v_m| = sqrt((l w c)^2 + v_x^2)        (pole-mass velocity)
+//     q_x    = u + fric_k tanh(v / v_cut) + k30 |v_m| v_x + m_1 l w^2 c + spring(b_x)         (generalised forces)
+//     q_th   = k30 l |v_m| proj - l g m_1 c
+//     b_x''  = (q_x + q_th s / l) / D
+//     th''   = (q_x s / l + q_th kappa) / D
+// which is single_pendulum_dynamics.hpp:13-186 with every parameter-only product folded into DynConst and the common
+// factor m_1 cancelled from numerator and determinant: 100 FP64 instructions per evaluation instead of 110, 141 instead
+// of 172 with the Jacobian rows, one reciprocal.  Against the generated code the operations are re-associated (the
+// results agree to a few ulp; tests/native/dynamics_check.cc holds both forms against the oracle's restatement, which is
+// bit-equal to the reference).
+//
 // Accelerations (b_x'', th'') at state (b_x, th, b_x', th') and control u.  FORCES selects the simulator variant that
 // takes external forces on the base (x component only is used by the model) and on the pole mass.
 template <bool FORCES>
-__device__ __forceinline__ void dyn_eval(const DynConst& P, const double b_x, const double th, const double b_xd,
-                                         const double thd, const double u, const double fb_x, const double fm_x,
-                                         const double fm_y, double& acc_x, double& acc_th) {
-  // four independent chains start here: sincos(th), tanh(friction), bumper springs, and (after sin) 1/det
+CPMPC_DEV void dyn_eval(const DynConst& P, const double b_x, const double th, const double b_xd, const double thd,
+                        const double u, const double fb_x, const double fm_x, const double fm_y, double& acc_x,
+                        double& acc_th) {
+  // four independent chains start here: sincos(th), tanh(friction), bumper springs, and (after sin) 1/D
   double s, c;
   fm::sincos_bf(th, s, c);
   const double fric = fm::tanh_bf(b_xd * P.inv_v_cut);
-  const double over_r = b_x - P.x_s;
-  const double pen_r = (0.0 < over_r) ? over_r : 0.0;
-  const double over_l = -(b_x + P.x_s);
-  const double pen_l = (0.0 < over_l) ? over_l : 0.0;
+  // one-sided bumper springs at +-x_s: force -sign(b_x) k_s max(|b_x| - x_s, 0)
+  const double over = fabs(b_x) - P.x_s;
+  const double pen = (0.0 < over) ? over : 0.0;
+  const double ks_signed = copysign(P.k_s, -b_x);
 
-  const double s_m1 = s * P.m1;
-  const double det = P.m1 * (P.m_total - s_m1 * s);
-  const double inv_det = fm::rcp(det);
+  const double D = fma(-P.m1, s * s, P.m_total);
+  const double inv_d = fm::rcp(D);
 
   const double lw = thd * P.len;
   const double cc = c * c;
@@ -124,44 +172,38 @@ __device__ __forceinline__ void dyn_eval(const DynConst& P, const double b_x, co
   const double speed_sq = lw * lw_cc + vx * vx;
   double speed, inv_speed;
   fm::sqrt_rsqrt(speed_sq, speed, inv_speed);
-  const double speed15 = 1.5 * speed;
+  const double spd = (0.0 < speed_sq) ? speed : 0.0;  // sqrt_rsqrt(0) is NaN
   const double proj = lw_cc - vx * s;
-  const bool moving = 0.0 < speed_sq;
-  const double drag_x = moving ? (vx * 2.0) * speed15 : 0.0;
-  const double drag_th = moving ? proj * P.len2 * speed15 : 0.0;
 
-  double q_th, q_x;
+  double q_th = proj * (spd * P.k30len) + c * P.nlgm;
+  double q_x = u + fric * P.fric_k + vx * (spd * P.k30) + (thd * P.m1len) * (thd * c) + ks_signed * pen;
   if (FORCES) {
-    q_th = drag_th * P.drag_k + P.len * (c * (fm_y - P.grav * P.m1) - fm_x * s);
-    q_x = u + fb_x + fm_x + fric * P.fric_k + drag_x * P.drag_k + P.m1 * lw * (thd * c) + P.k_s * (pen_l - pen_r);
-  } else {
-    q_th = drag_th * P.drag_k + P.len * (c * (-(P.grav * P.m1)));
-    q_x = u + fric * P.fric_k + drag_x * P.drag_k + P.m1 * lw * (thd * c) + P.k_s * (pen_l - pen_r);
+    q_th += P.len * (c * fm_y - fm_x * s);
+    q_x += fb_x + fm_x;
   }
-  const double num_th = q_x * (P.inv_len * s_m1) + q_th * P.m_over_l2;
-  const double num_x = q_x + q_th * (s * P.inv_len);
-  acc_x = num_x * (P.m1 * inv_det);
-  acc_th = inv_det * num_th;
+  const double s_over_l = s * P.inv_len;
+  acc_x = (q_x + q_th * s_over_l) * inv_d;
+  acc_th = (q_x * s_over_l + q_th * P.kappa) * inv_d;
 }
 
 // Accelerations plus rows 2-3 of d(x_dot)/dx (fx[4], fth[4]) and the two non-zero entries of d(x_dot)/du.
 // External forces are zero (the optimiser never passes any, optimization.cc:124-126).
-__device__ __forceinline__ void dyn_eval_jac(const DynConst& P, const double b_x, const double th, const double b_xd,
-                                             const double thd, const double u, double& acc_x, double& acc_th,
-                                             double fx[4], double fth[4], double& gx, double& gth) {
+//   d|v_m|/d(th, v, w) = (-l w c v_rel, v_x, l proj) / |v_m|   with v_rel = v_x + l w s
+//   d v_x /d(th, v, w) = (-l w c, 1, -l s),   d proj/d(th, v, w) = (-c v_rel, -s, l)
+// and d(b_x'')/dxi = (d num_x/dxi - b_x'' dD/dxi) / D with dD/dth = -2 m_1 s c (likewise th'').
+CPMPC_DEV void dyn_eval_jac(const DynConst& P, const double b_x, const double th, const double b_xd, const double thd,
+                            const double u, double& acc_x, double& acc_th, double fx[4], double fth[4], double& gx,
+                            double& gth) {
   double s, c;
   fm::sincos_bf(th, s, c);
   const double fric = fm::tanh_bf(b_xd * P.inv_v_cut);
-  const double over_r = b_x - P.x_s;
-  const bool act_r = 0.0 < over_r;
-  const double pen_r = act_r ? over_r : 0.0;
-  const double over_l = -(b_x + P.x_s);
-  const bool act_l = 0.0 < over_l;
-  const double pen_l = act_l ? over_l : 0.0;
+  const double over = fabs(b_x) - P.x_s;
+  const bool act = 0.0 < over;
+  const double pen = act ? over : 0.0;
+  const double ks_signed = copysign(P.k_s, -b_x);
 
-  const double s_m1 = s * P.m1;
-  const double det = P.m1 * (P.m_total - s_m1 * s);
-  const double inv_det = fm::rcp(det);
+  const double D = fma(-P.m1, s * s, P.m_total);
+  const double inv_d = fm::rcp(D);
 
   const double lw = thd * P.len;
   const double cc = c * c;
@@ -170,62 +212,52 @@ __device__ __forceinline__ void dyn_eval_jac(const DynConst& P, const double b_x
   const double speed_sq = lw * lw_cc + vx * vx;
   double speed, inv_speed;
   fm::sqrt_rsqrt(speed_sq, speed, inv_speed);
-  const double speed15 = 1.5 * speed;
-  const double vx2 = vx * 2.0;
-  const double proj = lw_cc - vx * s;
   const bool moving = 0.0 < speed_sq;
-  const double drag_x = moving ? vx2 * speed15 : 0.0;
-  const double drag_th = moving ? proj * P.len2 * speed15 : 0.0;
+  const double spd = moving ? speed : 0.0;       // every drag term and derivative below vanishes at rest
+  const double ispd = moving ? inv_speed : 0.0;
+  const double proj = lw_cc - vx * s;
 
-  const double gm1 = P.grav * P.m1;
-  const double q_th = drag_th * P.drag_k - P.len * (c * gm1);
-  const double q_x = u + fric * P.fric_k + drag_x * P.drag_k + P.m1 * lw * (thd * c) + P.k_s * (pen_l - pen_r);
-  const double s_m1_over_l = P.inv_len * s_m1;
+  const double m1lw = thd * P.m1len;
+  const double q_th = proj * (spd * P.k30len) + c * P.nlgm;
+  const double q_x = u + fric * P.fric_k + vx * (spd * P.k30) + m1lw * (thd * c) + ks_signed * pen;
   const double s_over_l = s * P.inv_len;
-  const double inv_det_l = inv_det * P.inv_len;
-  const double num_th = q_x * s_m1_over_l + q_th * P.m_over_l2;
-  const double num_x = q_x + q_th * s_over_l;
-  gth = s_m1 * inv_det_l;
-  gx = P.m1 * inv_det;
-  acc_x = num_x * gx;
-  acc_th = inv_det * num_th;
+  acc_x = (q_x + q_th * s_over_l) * inv_d;
+  acc_th = (q_x * s_over_l + q_th * P.kappa) * inv_d;
+  gx = inv_d;
+  gth = s_over_l * inv_d;
 
-  // derivatives of the drag terms (zero at rest): computed unconditionally, selected at the end
-  const double proj_n = 1.5 * (inv_speed * proj);
-  const double vx_rel = vx + s * lw;
-  const double speed3 = speed * 3.0;
-  const double d_th_q = moving ? -((lw * proj_n + speed15) * (c * P.len) * (2.0 * vx_rel)) : 0.0;
-  const double d_th_x = moving ? -((inv_speed * vx_rel * (vx2 * 1.5) + speed3) * lw * c) : 0.0;
-  const double d_v_l = moving ? P.len * (vx2 * proj_n - speed3 * s) : 0.0;
-  const double d_v_x = moving ? vx2 * vx2 * (0.75 * inv_speed) + speed3 : 0.0;
-  const double d_w_th = moving ? P.len * (proj * proj_n + (cc + s * s) * speed15) * P.len2 : 0.0;
+  // derivatives of the two drag terms T_x = k30 |v_m| v_x and T_th = k30 l |v_m| proj
+  const double vx_rel = vx + lw * s;
+  const double ivx = ispd * vx;
+  const double ipr = ispd * proj;
+  const double tx_th = -(((lw * c) * P.k30) * (spd + ivx * vx_rel));
+  const double tx_v = P.k30 * (spd + ivx * vx);
+  const double x_w = P.k30len * (ivx * proj - s * spd);  // dT_x/dw == dT_th/dv
+  const double tth_th = -(((c * vx_rel) * P.k30len) * (spd + ipr * lw));
+  const double tth_w = P.k30len2 * (spd + ipr * proj);
 
-  const double dq_th_dth = d_th_q * P.drag_k + P.len * (s * gm1);
-  const double dq_x_dth = d_th_x * P.drag_k - lw * s_m1 * thd;
-  const double m1_c = P.m1 * c;
-  const double dv_l_k = d_v_l * P.drag_k;
-  const double inv_det_sq = inv_det * inv_det;
-  const double dq_x_dw = 2.0 * lw * m1_c + dv_l_k;
-  const double dw_th_k = d_w_th * P.drag_k;
-  const double dq_x_dv = P.inv_v_cut * (1.0 - fric * fric) * P.fric_k + d_v_x * P.drag_k;
-  const double spring_sw = P.k_s * ((act_l ? -1.0 : 0.0) - (act_r ? 1.0 : 0.0));
+  const double dq_x_dv = P.fric_kv * (1.0 - fric * fric) + tx_v;
+  const double dq_x_dth = tx_th - (m1lw * thd) * s;
+  const double dq_x_dw = (m1lw + m1lw) * c + x_w;
+  const double dq_th_dth = tth_th - s * P.nlgm;
+  const double spring_sw = act ? -P.k_s : 0.0;
+  const double c_over_l = c * P.inv_len;
+  const double msc2 = (P.m1x2 * s) * c;  // -dD/dth
 
-  fx[0] = gx * spring_sw;
-  fx[1] = P.m1 * (num_x * s_m1 * m1_c * (2.0 * inv_det_sq) +
-                  inv_det * (dq_x_dth + P.inv_len * (s * dq_th_dth + c * q_th)));
-  fx[2] = (dq_x_dv + s_over_l * dv_l_k) * gx;
-  fx[3] = (dq_x_dw + s_over_l * dw_th_k) * gx;
+  fx[0] = spring_sw * inv_d;
   fth[0] = spring_sw * gth;
-  fth[1] = inv_det * dq_th_dth * P.m_over_l2 +
-           P.m1 * (inv_det_sq * num_th * s_m1 * (c * 2.0) + (c * q_x + s * dq_x_dth) * inv_det_l);
-  fth[2] = inv_det * (P.m_over_l2 * dv_l_k + dq_x_dv * s_m1_over_l);
-  fth[3] = inv_det * (P.m_over_l2 * dw_th_k + dq_x_dw * s_m1_over_l);
+  fx[1] = (dq_x_dth + dq_th_dth * s_over_l + q_th * c_over_l + acc_x * msc2) * inv_d;
+  fth[1] = (dq_x_dth * s_over_l + q_x * c_over_l + dq_th_dth * P.kappa + acc_th * msc2) * inv_d;
+  fx[2] = (dq_x_dv + x_w * s_over_l) * inv_d;
+  fth[2] = (dq_x_dv * s_over_l + x_w * P.kappa) * inv_d;
+  fx[3] = (dq_x_dw + tth_w * s_over_l) * inv_d;
+  fth[3] = (dq_x_dw * s_over_l + tth_w * P.kappa) * inv_d;
 }
 
 // One classic RK4 step, in place, no Jacobians (integration.hpp:53-62).  The four stages run as a rolled loop around
 // ONE inlined copy of the dynamics so the hot code stays inside the instruction cache.
 template <bool FORCES>
-__device__ __forceinline__ void rk4_step(const DynConst& P, double x[4], const double u, const double h,
+CPMPC_DEV void rk4_step(const DynConst& P, double x[4], const double u, const double h,
                                          const double fb_x = 0.0, const double fm_x = 0.0, const double fm_y = 0.0) {
   const double hh = h * 0.5;
   double a0 = x[0], a1 = x[1], a2 = x[2], a3 = x[3];  // stage argument
@@ -257,7 +289,7 @@ __device__ __forceinline__ void rk4_step(const DynConst& P, double x[4], const d
 // A = d x+ / d x (4x4 row-major), Bv = d x+ / d u.  Stage Jacobians have the structure
 // F = [[0 0 1 0],[0 0 0 1],[fx],[fth]], Fu = [0 0 gx gth]; the chain rule K_i = F_i (I + c_i K_{i-1}) and
 // ku_i = F_i ku_{i-1} c_i + Fu_i is carried through a rolled stage loop.
-__device__ __forceinline__ void rk4_step_jac(const DynConst& P, double x[4], const double u, const double h,
+CPMPC_DEV void rk4_step_jac(const DynConst& P, double x[4], const double u, const double h,
                                              double A[16], double Bv[4]) {
   const double hh = h * 0.5;
   double a0 = x[0], a1 = x[1], a2 = x[2], a3 = x[3];

@@ -63,11 +63,11 @@ struct DoublePlant {
 };
 
 struct SinglePlant {
-  static constexpr int NX = 4, NQ = 2, NP = CPMPC_DYN_STRIDE, NC = 12;
+  static constexpr int NX = 4, NQ = 2, NP = CPMPC_DYN_STRIDE, NC = DYN_CONST_DOUBLES;
   using Const = DynConst;
   __device__ __forceinline__ static Const make(const double* __restrict__ p) { return make_dyn_const(p); }
   __device__ __forceinline__ static Const dummy() {
-    return Const{1.0, 2.0, 1.0, 1.0, 2.0, 2.0, 0.0, 0.0, 1.0, 0.0, 1.0, 9.81};
+    return dummy_dyn_const();
   }
   __device__ __forceinline__ static void store(double* d, const Const& c) { store_dyn_const(d, c); }
   __device__ __forceinline__ static void load(Const& c, const double* s) { load_dyn_const(c, s); }

@@ -53,7 +53,7 @@ struct KernelCfg {
   int nchunk;  // nseg * cps
   int stride;  // doubles of shared memory per instance
   int off_xs, off_u, off_dxs, off_du, off_phi, off_e, off_gam, off_xk, off_phic, off_aug;
-  int off_dyn;  // this instance's DynConst (12 doubles): phase functions reload it instead of pinning registers
+  int off_dyn;  // this instance's DynConst (DYN_CONST_DOUBLES doubles): phase functions reload it instead of pinning registers
   int off_xc, off_uc, off_xkc;  // line-search candidates: alias the Gamma block (dead after the QP)
   int kk_stride;                // doubles of global scratch per group: W * GAIN_STRIDE Riccati feedback rows
   double dt, rel_tol, first_tol, abs_tol, pen_init, pen_scale, rho, armijo_c1;
@@ -1510,7 +1510,7 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
       for (int i = 0; i < 4; ++i) x_cur[i] = ps[i];
       set_point = io.set_points[inst];
     } else {
-      if (c.gl == 0) store_dyn_const(c.sm + cfg.off_dyn, DynConst{1.0, 2.0, 1.0, 1.0, 2.0, 2.0, 0.0, 0.0, 1.0, 0.0, 1.0, 9.81});
+      if (c.gl == 0) store_dyn_const(c.sm + cfg.off_dyn, dummy_dyn_const());
       w.w_u = w.w_r = 1.0;
       w.wt[0] = w.wt[1] = w.wt[2] = w.wt[3] = 1.0;
     }

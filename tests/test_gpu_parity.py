@@ -255,7 +255,10 @@ def test_variants_against_compiled_reference_live(oracle, over, min_frac):
     if not oracle.ref_available():
         pytest.skip("oracle/_ref/libref.so not present")
     from cart_pole_mpc_b200 import synthetic
-    B = 256
+    # 1024 instances: the sampling noise of a pass fraction near 0.95 is 0.7 % (1.4 % on the 256 instances this test
+    # used before, which put the single-shooting variant within a standard deviation of its bar: profiles/parity_ab.py
+    # prints the fractions of a build on this sample)
+    B = 1024
     st, dy, sp = synthetic.swingup_batch(B, seed=17)
     sp = sp + np.linspace(-0.3, 0.3, B)  # non-zero set points as well
     with oracle.using_ref():
