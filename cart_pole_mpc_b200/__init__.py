@@ -6,9 +6,9 @@ host API over that ABI; pypendulum.py mirrors the reference's Python module; hos
 the reference's struct/class API.  Importing this package never touches oracle/.
 """
 from .batched import (BatchedOptimization, StepOutputs, TERMINATION_NAMES, STEP_RESULT_NAMES, make_params,
-                      measure_fp64_peak, sim_step, launch_count)
+                      measure_fp64_peak, sim_step, launch_count, debug_fastmath)
 
 from .plant import PlantBatchedOptimization, make_plant_params
 
 __all__ = ["PlantBatchedOptimization", "make_plant_params", "BatchedOptimization", "StepOutputs", "TERMINATION_NAMES", "STEP_RESULT_NAMES", "make_params",
-           "measure_fp64_peak", "sim_step", "launch_count"]
+           "measure_fp64_peak", "sim_step", "launch_count", "debug_fastmath"]

@@ -268,5 +268,13 @@ def measure_fp64_peak(device: int = 0) -> float:
     return out.value
 
 
+def debug_fastmath(x, device: int = 0) -> np.ndarray:
+    """{sin, cos, tanh, 1/x, sqrt|x|, 1/sqrt|x|} of every x as the DEVICE evaluates them (csrc/fastmath.cuh): [n, 6]."""
+    xx = np.ascontiguousarray(x, dtype=np.float64).ravel()
+    out = np.empty((xx.size, 6), dtype=np.float64)
+    _capi.check(_capi.lib().cpmpc_debug_fastmath(int(device), xx.size, xx.ctypes.data, out.ctypes.data))
+    return out
+
+
 def launch_count() -> int:
     return int(_capi.lib().cpmpc_launch_count())

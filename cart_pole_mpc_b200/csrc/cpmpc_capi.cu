@@ -964,6 +964,29 @@ int cpmpc_debug_first_qp(cpmpc_handle h, const double* states, const double* dyn
   return rc;
 }
 
+int cpmpc_debug_fastmath(int device, int64_t n, const double* x, double* out) {
+  if (n < 0 || (n > 0 && (x == nullptr || out == nullptr))) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "bad arguments");
+  if (n == 0) return CPMPC_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  double *d_x = nullptr, *d_out = nullptr;
+  struct Free {
+    double*& a;
+    double*& b;
+    ~Free() {
+      cudaFree(a);
+      cudaFree(b);
+    }
+  } guard{d_x, d_out};
+  CUDA_TRY(cudaMalloc(&d_x, sizeof(double) * n));
+  CUDA_TRY(cudaMalloc(&d_out, sizeof(double) * n * 6));
+  CUDA_TRY(cudaMemcpy(d_x, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+  cpmpc_fastmath_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(n, d_x, d_out);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(out, d_out, sizeof(double) * n * 6, cudaMemcpyDeviceToHost));
+  return CPMPC_OK;
+}
+
 int cpmpc_measure_fp64_peak(int device, double* tflops_out) {
   if (tflops_out == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "null argument");
   CUDA_TRY(cudaSetDevice(device));

@@ -1728,6 +1728,24 @@ __global__ void cpmpc_sim_kernel(const long long B, double* __restrict__ states,
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// The elementary functions of fastmath.cuh as the device evaluates them (cpmpc_debug_fastmath).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void cpmpc_fastmath_kernel(const long long n, const double* __restrict__ x, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = x[i];
+  double s, c, root, inv_root;
+  fm::sincos_bf(v, s, c);
+  fm::sqrt_rsqrt(fabs(v), root, inv_root);
+  out[6 * i] = s;
+  out[6 * i + 1] = c;
+  out[6 * i + 2] = fm::tanh_bf(v);
+  out[6 * i + 3] = fm::rcp(v);
+  out[6 * i + 4] = root;
+  out[6 * i + 5] = inv_root;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // FP64 FMA throughput probe: 8 independent register-resident DFMA chains per thread.
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void cpmpc_dfma_probe_kernel(double* out, const int iters, const double a, const double b) {

@@ -217,6 +217,12 @@ int64_t cpmpc_launch_count(void);
  * it in *tflops_out (2 flops per FMA).  Used as the roofline denominator (MEASURED_PEAKS.json has no FP64 entry). */
 int cpmpc_measure_fp64_peak(int device, double* tflops_out);
 
+/* Debug view of the device's elementary functions (csrc/fastmath.cuh: the branch-free sin/cos, tanh, reciprocal and
+ * square root the dynamics evaluate): for every x[i] writes {sin x, cos x, tanh x, 1/x, sqrt|x|, 1/sqrt|x|} to
+ * out[6 i ...], computed ON THE DEVICE with the hardware seed instructions.  HOST buffers.  The reference has no
+ * counterpart (it calls libm); tests compare with libm at the ulp level. */
+int cpmpc_debug_fastmath(int device, int64_t n, const double* x, double* out);
+
 /* ---------------------------------------------------------------------------------------------------------------------
  * Plant-generic entry points: the same controller over a plant with NX states per shooting node.  They exist for the
  * cart-mounted DOUBLE pendulum (BASELINE.json configs[4]).  The reference holds only its physics spec

@@ -799,9 +799,11 @@ def test_pipelined_steps_equal_synchronous_steps():
     s.wait()
     s.wait()  # nothing in flight: no-op
     for t in range(T):
-        assert np.array_equal(u[t], want[t].u), t
-        assert np.array_equal(pred[t], want[t].predicted_states), t
-        assert np.array_equal(stats[t].view(_capi.STATS_DTYPE), want[t].stats), t
+        # equal_nan: an instance that ends a step with QP_INDEFINITE warm-starts the next one from clamped controls, its
+        # rollout overflows and the step is rejected with non-finite predicted states — in both chains alike
+        assert np.array_equal(u[t], want[t].u, equal_nan=True), t
+        assert np.array_equal(pred[t], want[t].predicted_states, equal_nan=True), t
+        assert stats[t].tobytes() == want[t].stats.tobytes(), t
     # cold steps through the flag, without waiting in between (the third call retires the first by itself)
     for t in range(3):
         s.step_async(ins[2], dyp, spp, u[t], reset=True)
