@@ -34,53 +34,53 @@ namespace fm {
 // whereas a constant-bank table is fetched into uniform registers two doubles per LDCU.128.
 #define CPMPC_FM_CONSTS(X) \
   X(pio2_2, 0x1.5110b4611a626p-22) \
-  X(pio2_3, 0x1.98a2e03707345p-77) \
-  X(s5, -2.50507602534068634195e-08) \
-  X(s4, 2.75573137070700676789e-06) \
-  X(s3, -1.98412698298579493134e-04) \
-  X(s2, 8.33333333332248946124e-03) \
-  X(s1, -1.66666666666666324348e-01) \
-  X(c5, 2.08757232129817482790e-09) \
-  X(c4, -2.75573143513906633035e-07) \
-  X(c3, 2.48015872894767294178e-05) \
-  X(c2, -1.38888888888741095749e-03) \
-  X(c1, 4.16666666666666019037e-02) \
   X(ln2_lo, -0x1.05c610ca86c39p-29) \
-  X(e8, 1.0 / 40320.0) \
-  X(e6, 1.0 / 720.0) \
-  X(e4, 1.0 / 24.0) \
-  X(e9, 1.0 / 362880.0) \
-  X(e7, 1.0 / 5040.0) \
-  X(e5, 1.0 / 120.0) \
-  X(e3, 1.0 / 6.0)
+  X(s5, -2.50507602534068634195e-08) \
+  X(c5, 2.08757232129817482790e-09) \
+  X(s4, 2.75573137070700676789e-06) \
+  X(c4, -2.75573143513906633035e-07) \
+  X(s3, -1.98412698298579493134e-04) \
+  X(c3, 2.48015872894767294178e-05) \
+  X(s2, 8.33333333332248946124e-03) \
+  X(c2, -1.38888888888741095749e-03) \
+  X(s1, -1.66666666666666324348e-01) \
+  X(c1, 4.16666666666666019037e-02) \
+  X(x8, 0x1.a01991399f987p-16) \
+  X(x9, 0x1.71ddf52ded199p-19) \
+  X(x6, 0x1.6c16c18826db1p-10) \
+  X(x7, 0x1.a01a01b15de9dp-13) \
+  X(x4, 0x1.555555554f000p-5) \
+  X(x5, 0x1.111111110f1e5p-7) \
+  X(x2, 0x1.0000000000011p-1) \
+  X(x3, 0x1.555555555555ap-3)
+// (the table is ordered in 16-byte pairs of constants that are consumed at the same time — the sine and cosine chains
+// and the even and odd halves of the exp polynomial advance in step — so that each LDCU.128 is live for one step only)
 // Five FMAs of the chains below take TWO constants (the start of each Horner chain, fma(z, c_top, c_next), and the
 // 1.5 * 2^52 rounding trick), and an FP64 instruction takes at most ONE operand from the constant bank or a uniform
 // register: the other had to sit in an ordinary register, which ptxas either hoisted out of the caller's stage loop
 // (ten registers held across the whole rollout) or, under register pressure, re-loaded with LDC.64 in every dynamics
 // evaluation right in front of its use, on the critical path (the linearisation loop; and the merit loop flipped
 // between the two with unrelated changes elsewhere in the solver).  A double whose low 32 bits are zero is encodable
-// as an IMMEDIATE operand instead.  The magic number is such a value; the four top polynomial coefficients are rounded
-// to 21 significant bits here: each multiplies the highest power of a reduced argument, so the change is below 3e-18
+// as an IMMEDIATE operand instead.  The magic number is such a value; the top coefficients of the sine and cosine
+// polynomials are rounded to 21 significant bits here: each multiplies the highest power of a reduced argument, so the change is below 3e-18
 // relative to the result (0.03 ulp; tests/test_fastmath.py holds the functions to the same bounds as before).
 // The same encoding serves wherever 21 bits are enough or the remainder can go into the next term:
 //   * 2/pi and log2(e) only pick the integer k of the range reduction; a relative error of 3e-7 moves the reduced
 //     argument at most 1e-4 beyond its nominal interval, where the polynomials are as accurate as inside;
-//   * pi/2 = kPio2Hi + pio2_2 + pio2_3 and ln 2 = kLn2Hi + ln2_lo are split so that the leading part is an immediate
-//     (k * leading part is exact in the FMA either way; the sums carry 127 and 74 bits);
-//   * 1/10! and 1/11! multiply r^10 and r^11 with |r| <= ln2 / 2 (2e-18 relative to exp(r)).
+//   * pi/2 = kPio2Hi + pio2_2 and ln 2 = kLn2Hi + ln2_lo are split so that the leading part is an immediate
+//     (k * leading part is exact in the FMA either way; both sums carry 74 bits);
+//   * the two top coefficients of the exp polynomial multiply r^10 and r^11 with |r| <= ln2 / 2 (2e-18 relative).
 constexpr double kTwoOverPi = 0x1.45f3p-1;          // 2 / pi to 21 bits
 constexpr double kPio2Hi = 0x1.921fbp+0;            // pi / 2 to 21 bits
 constexpr double kLog2e = 0x1.71547p+0;             // log2(e) to 21 bits
 constexpr double kLn2Hi = 0x1.62e43p-1;             // ln 2 to 21 bits
-constexpr double kE10 = 0x1.27e5p-22;               // 1 / 10! to 21 bits
-constexpr double kE11 = 0x1.ae645p-26;              // 1 / 11! to 21 bits
+constexpr double kX10 = 0x1.28b47p-22;              // degree-10 and -11 coefficients of the exp polynomial (below), 21 bits
+constexpr double kX11 = 0x1.af63ap-26;
 constexpr double kMagic = 0x1.8p+52;                // 1.5 * 2^52
 constexpr double kS6 = 0x1.5d93ap-33;               // 1.58969099521155010221e-10 (fdlibm S6) to 21 bits
 constexpr double kC6 = -0x1.8fae9p-37;              // -1.13596475577881948265e-11 (fdlibm C6) to 21 bits
-constexpr double kE12 = 0x1.1eed8p-29;              // 1 / 12! to 21 bits
-constexpr double kE13 = 0x1.61246p-33;              // 1 / 13! to 21 bits
 
-struct FmConsts {
+struct alignas(16) FmConsts {
 #define CPMPC_X(name, value) double name;
   CPMPC_FM_CONSTS(CPMPC_X)
 #undef CPMPC_X
@@ -171,10 +171,10 @@ CPMPC_HD void sincos_bf(double x, double& s_out, double& c_out) {
   memcpy(&tb, &t, sizeof(tb));
 #endif
   const int q = (int)(tb & 3);
-  // Cody-Waite with a three-part pi/2 (the FMAs keep the products exact)
+  // Cody-Waite with pi/2 = kPio2Hi (21 bits: k * kPio2Hi is exact) + pio2_2 (53 bits): 74 bits of pi/2, i.e. an
+  // absolute error of k * 4e-23 in the reduced argument (3e-17 at the |x| = 2^20 end of the supported range)
   double r = CPMPC_FMA(-kd, kPio2Hi, x);
   r = CPMPC_FMA(-kd, CPMPC_K(pio2_2), r);
-  r = CPMPC_FMA(-kd, CPMPC_K(pio2_3), r);
   const double z = r * r;
   // fdlibm kernel polynomials on |r| <= pi/4
   double ps = CPMPC_FMA(z, kS6, CPMPC_K(s5));
@@ -215,19 +215,18 @@ CPMPC_HD double tanh_bf(double x) {
   const int n = (int)(int32_t)(tb & 0xffffffff);  // in [-58, 0]
   double r = CPMPC_FMA(-nd, kLn2Hi, y);
   r = CPMPC_FMA(-nd, CPMPC_K(ln2_lo), r);
-  // exp(r), |r| <= ln2/2: Taylor to r^13, even/odd split to halve the dependent depth
+  // exp(r), |r| <= ln2/2: degree-11 polynomial through the Chebyshev nodes of the interval (relative error 1.4e-17
+  // with these coefficients; tests/prototypes/exp_poly.py), even/odd split to halve the dependent depth
   const double r2 = r * r;
-  double pe = CPMPC_FMA(r2, kE12, kE10);  // r^12, r^10
-  pe = CPMPC_FMA(r2, pe, CPMPC_K(e8));
-  pe = CPMPC_FMA(r2, pe, CPMPC_K(e6));
-  pe = CPMPC_FMA(r2, pe, CPMPC_K(e4));
-  pe = CPMPC_FMA(r2, pe, 0.5);
+  double pe = CPMPC_FMA(r2, kX10, CPMPC_K(x8));
+  pe = CPMPC_FMA(r2, pe, CPMPC_K(x6));
+  pe = CPMPC_FMA(r2, pe, CPMPC_K(x4));
+  pe = CPMPC_FMA(r2, pe, CPMPC_K(x2));
   pe = CPMPC_FMA(r2, pe, 1.0);
-  double po = CPMPC_FMA(r2, kE13, kE11);  // r^13, r^11
-  po = CPMPC_FMA(r2, po, CPMPC_K(e9));
-  po = CPMPC_FMA(r2, po, CPMPC_K(e7));
-  po = CPMPC_FMA(r2, po, CPMPC_K(e5));
-  po = CPMPC_FMA(r2, po, CPMPC_K(e3));
+  double po = CPMPC_FMA(r2, kX11, CPMPC_K(x9));
+  po = CPMPC_FMA(r2, po, CPMPC_K(x7));
+  po = CPMPC_FMA(r2, po, CPMPC_K(x5));
+  po = CPMPC_FMA(r2, po, CPMPC_K(x3));
   po = CPMPC_FMA(r2, po, 1.0);
   const double er = CPMPC_FMA(r, po, pe);
   // scale by 2^n (n in [-58, 0]: always a normal number)
