@@ -140,28 +140,29 @@ template <int L>
 __device__ __forceinline__ double control_cost_partial(const Ctx& c, const Weights& w, const double* uu,
                                                        const double u_prev) {
   const KernelCfg& k = *c.cfg;
-  double f = 0.0;
-    for (int s = c.gl; s < k.nseg; s += L) {
-        for (int i = 0; i < k.S; ++i) {
-      const int col = s * k.S + i;
+  // Branch-free: an absent cost family has weight 0 (its residuals add +0), the rate residual behind the last knot is
+  // formed against the knot itself (0), and the one against the previous step's control is added on the lane that owns
+  // knot 0.  The squares of the two families go to separate accumulators (two short dependent chains instead of one
+  // chain through every term and a branch per term).
+  double f_r = 0.0, f_u = 0.0;
+  for (int s = c.gl; s < k.nseg; s += L) {
+    const int c0 = s * k.S;
+    #pragma unroll 2
+    for (int i = 0; i < k.S; ++i) {
+      const int col = c0 + i;
       const double uk = uu[col];
-      if (w.w_r > 0.0) {
-        if (col + 1 < k.W) {
-          const double r = (uk - uu[col + 1]) * w.w_r;
-          f += 0.5 * (r * r);
-        }
-        if (col == 0) {
-          const double r = (uk - u_prev) * w.w_r;
-          f += 0.5 * (r * r);
-        }
-      }
-      if (w.w_u > 0.0) {
-        const double r = uk * w.w_u;
-        f += 0.5 * (r * r);
-      }
+      const double un = uu[(col + 1 < k.W) ? col + 1 : col];
+      const double rr = (uk - un) * w.w_r;
+      const double ru = uk * w.w_u;
+      f_r = fma(rr, rr, f_r);
+      f_u = fma(ru, ru, f_u);
     }
   }
-  return f;
+  if (c.gl == 0) {
+    const double r0 = (uu[0] - u_prev) * w.w_r;
+    f_r = fma(r0, r0, f_r);
+  }
+  return 0.5 * (f_r + f_u);
 }
 
 // Terminal cost / terminal equality / initial-state equality residuals (optimization.cc:228-267), evaluated by
@@ -769,7 +770,7 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, boo
     } else {
       const double dd = w.wt[i] * w.wt[i];
       if (dd > 0.0) {
-        invd = 1.0 / dd;
+        invd = fm::rcp(dd);
         off = m[i] + d;  // (w^2 d) / w^2
       } else {
         invd = -1.0;  // zero weight: the row does not exist
@@ -970,18 +971,15 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
 
   // gradient of the control costs at the current controls into du[] (the QP routines consume and overwrite it)
   auto fill_gradient = [&]() {
+    // branch-free (weights of absent cost families are 0): the rate residual behind the last knot is formed against the
+    // knot itself, the one in front of knot 0 against the previous step's control
+    const double wr2 = w.w_r * w.w_r, wu2 = w.w_u * w.w_u;
     #pragma unroll 1
     for (int col = c.gl; col < W; col += L) {
-      double g = 0.0;
       const double uk = u[col];
-      if (w.w_r > 0.0) {
-        const double wr2 = w.w_r * w.w_r;
-        if (col + 1 < W) g += wr2 * (uk - u[col + 1]);
-        if (col > 0) g -= wr2 * (u[col - 1] - uk);
-        if (col == 0) g += wr2 * (uk - u_prev);
-      }
-      if (w.w_u > 0.0) g += (w.w_u * w.w_u) * uk;
-      du[col] = g;
+      const double un = u[(col + 1 < W) ? col + 1 : col];
+      const double up = (col > 0) ? u[col - 1] : u_prev;
+      du[col] = wr2 * (uk - un) + wr2 * (uk - up) + wu2 * uk;
     }
     CPMPC_GSYNC();
   };
@@ -1295,21 +1293,28 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
         // polynomial step-length selection (nonlinear.cc:418-443,531-605)
         double new_alpha = 0.0;
         bool valid;
+        // The quotients and the square root are the straight-line forms of fastmath.cuh (1 ulp; the IEEE division and
+        // square root of the CUDA math library carry slow-path branches, and every lane of the warp walks through this
+        // code in every trial: 2.7 % of the kernel's samples).  A zero or non-finite denominator yields a non-finite
+        // step length as it does with IEEE arithmetic, which the test below rejects.
         if (ls == 1) {
           const double numerator = phi_prev - dphi0 * a_prev - phi0;
           valid = !(dphi0 > 0.0 || numerator <= 0.0);
-          new_alpha = -dphi0 * a_prev * a_prev / (2.0 * numerator);
+          new_alpha = (-dphi0 * a_prev * a_prev) * fm::rcp(2.0 * numerator);
         } else {
           const double a0 = a_prev2, a1 = a_prev;
           const double m00 = a0 * a0 * a0, m01 = a0 * a0, m10 = a1 * a1 * a1, m11 = a1 * a1;
           const double r0 = phi_prev2 - phi0 - dphi0 * a0;
           const double r1 = phi_prev - phi0 - dphi0 * a1;
-          const double inv_det = 1.0 / (m00 * m11 - m10 * m01);
+          const double inv_det = fm::rcp(m00 * m11 - m10 * m01);
           const double ca = (m11 * inv_det) * r0 + (-m01 * inv_det) * r1;
           const double cb = (-m10 * inv_det) * r0 + (m00 * inv_det) * r1;
           const double arg_sqrt = cb * cb - 3.0 * ca * dphi0;
           valid = !(ca == 0.0 || arg_sqrt < -1.0e-12);
-          new_alpha = (-cb + sqrt(fmax(arg_sqrt, 0.0))) / (3.0 * ca);
+          double root, inv_root;
+          fm::sqrt_rsqrt(arg_sqrt, root, inv_root);
+          (void)inv_root;
+          new_alpha = (-cb + ((arg_sqrt > 0.0) ? root : 0.0)) * fm::rcp(3.0 * ca);
         }
         if (!valid || !isfinite(new_alpha) || new_alpha <= 0.0 || new_alpha >= alpha) {
           step_result = SR_INVALID_ALPHA;
