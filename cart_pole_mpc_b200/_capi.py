@@ -14,6 +14,8 @@ WEIGHTS_STRIDE = 6
 # every symbol include/cpmpc.h declares
 FLAG_LOW_LATENCY = 1  # CPMPC_FLAG_LOW_LATENCY
 FLAG_MIN_LATENCY = 2  # CPMPC_FLAG_MIN_LATENCY
+FLAG_SPLIT_LAUNCH = 4  # CPMPC_FLAG_SPLIT_LAUNCH
+FLAG_FUSED_LAUNCH = 8  # CPMPC_FLAG_FUSED_LAUNCH
 
 EXPORTED_SYMBOLS = (
     "cpmpc_last_error", "cpmpc_version", "cpmpc_default_params", "cpmpc_create", "cpmpc_create_ex", "cpmpc_destroy", "cpmpc_batch",

@@ -64,13 +64,17 @@ class BatchedOptimization:
     """
 
     def __init__(self, batch: int, params: Optional[_capi.CpmpcParams] = None, device: int = 0,
-                 low_latency: bool = False, min_latency: bool = False, **overrides):
+                 low_latency: bool = False, min_latency: bool = False, split_launch: Optional[bool] = None,
+                 **overrides):
         self._h = C.c_void_p()
         self._lib = _capi.lib()
         self.params = params if params is not None else make_params(**overrides)
         if params is not None and overrides:
             raise ValueError("pass either params or keyword overrides")
         flags = (_capi.FLAG_LOW_LATENCY if low_latency else 0) | (_capi.FLAG_MIN_LATENCY if min_latency else 0)
+        # launch shape (include/cpmpc.h): None = by batch size; the results are bit-identical either way
+        if split_launch is not None:
+            flags |= _capi.FLAG_SPLIT_LAUNCH if split_launch else _capi.FLAG_FUSED_LAUNCH
         _capi.check(self._lib.cpmpc_create_ex(C.byref(self.params), int(batch), int(device), flags,
                                               C.byref(self._h)))
         self.batch = int(batch)

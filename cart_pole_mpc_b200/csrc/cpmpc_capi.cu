@@ -64,6 +64,11 @@ struct cpmpc_solver {
   unsigned char* d_has_prev = nullptr;
   double* d_u_guess = nullptr;
   double* d_kk = nullptr;
+  // split launch (large batches): shooting states of the initial guess [B, 4 NS] from cpmpc_guess_kernel, and the
+  // controls for cpmpc_post_kernel when the caller asked for no u_out
+  bool split = false, split_loop = false;  // Step / closed loop
+  double* d_guess = nullptr;
+  double* d_u_split = nullptr;
   unsigned long long* d_queue = nullptr;
   double* d_iter_log = nullptr;
   bool log_enabled = false;
@@ -162,8 +167,29 @@ int Launch(cpmpc_solver* h, KernelIO io, cudaStream_t stream) {
   io.queue = h->d_queue;
   io.iter_log = h->log_enabled ? h->d_iter_log : nullptr;
   io.warp_cycles = h->d_warp_cycles;
-  fn<<<h->grid, 32 * h->warps_per_block, h->smem_bytes, stream>>>(h->cfg, io);
-  g_launches.fetch_add(1);
+  if (!(io.sim ? h->split_loop : h->split) || io.dbg != nullptr) {
+    fn<<<h->grid, 32 * h->warps_per_block, h->smem_bytes, stream>>>(h->cfg, io);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return CPMPC_OK;
+  }
+  // Split launch: guess rollouts (one thread per instance) -> SQP -> predicted states / plant step (one thread per
+  // instance), once per control tick, all stream-ordered.  Results are bit-identical to the fused kernel's.
+  if (io.u_out == nullptr) io.u_out = h->d_u_split;
+  const bool need_post = io.pred_out != nullptr || io.sim != 0;
+  const long long n_ticks = io.n_steps;
+  const unsigned wide_blocks = static_cast<unsigned>((h->B + 127) / 128);
+  io.n_steps_total = n_ticks;
+  io.n_steps = 1;
+  io.split = 1;
+  io.guess = h->d_guess;
+  for (long long tick = 0; tick < n_ticks; ++tick) {
+    io.step_index = tick;
+    cpmpc_guess_kernel<<<wide_blocks, 128, 0, stream>>>(h->cfg, io, h->d_guess);
+    fn<<<h->grid, 32 * h->warps_per_block, h->smem_bytes, stream>>>(h->cfg, io);
+    if (need_post) cpmpc_post_kernel<<<wide_blocks, 128, 0, stream>>>(h->cfg, io, io.u_out);
+    g_launches.fetch_add(need_post ? 3 : 2);
+  }
   CUDA_TRY(cudaGetLastError());
   return CPMPC_OK;
 }
@@ -511,6 +537,21 @@ int cpmpc_create_ex(const cpmpc_params* params, int64_t batch, int device, uint3
   CUDA_TRY(cudaMalloc(&h->d_kk, sizeof(double) * n_groups * k.kk_stride));
   CUDA_TRY(cudaMalloc(&h->d_warp_cycles, sizeof(unsigned long long) * WARP_REC * h->grid * wpb));
   CUDA_TRY(cudaMemset(h->d_warp_cycles, 0, sizeof(unsigned long long) * WARP_REC * h->grid * wpb));
+  // Large batches run the serial rollouts of a Step in their own one-thread-per-instance kernels (Launch).  "Large" =
+  // more instances than two full waves of the persistent grid: below that the step is the latency of ONE solve and
+  // two extra launches only add to it.  Results do not depend on the choice.
+  // The closed loop gains less (its fused form has no tail per control tick: warps run on into the next tick) and
+  // breaks even at about four waves (profiles/r02_v_ab_split.jsonl).
+  h->split = batch >= 2 * n_groups;
+  h->split_loop = batch >= 5 * n_groups;
+  if ((flags & CPMPC_FLAG_SPLIT_LAUNCH) != 0u) h->split = h->split_loop = true;
+  if ((flags & CPMPC_FLAG_FUSED_LAUNCH) != 0u) h->split = h->split_loop = false;
+  if (const char* env = std::getenv("CPMPC_SPLIT")) h->split = h->split_loop = std::atoi(env) != 0;
+  if (k.cps != 1) h->split = h->split_loop = false;  // the chunked linearisation wants the guess's chunk-start states
+  if (h->split || h->split_loop) {
+    CUDA_TRY(cudaMalloc(&h->d_guess, sizeof(double) * batch * 4 * k.NS));
+    CUDA_TRY(cudaMalloc(&h->d_u_split, sizeof(double) * batch * k.W));
+  }
   CUDA_TRY(cudaMalloc(&h->d_queue, sizeof(unsigned long long) * 2));
   CUDA_TRY(cudaMemset(h->d_queue, 0, sizeof(unsigned long long) * 2));
   CUDA_TRY(cudaMalloc(&h->d_u_guess, sizeof(double) * k.W));
@@ -535,6 +576,8 @@ int cpmpc_destroy(cpmpc_handle h) {
   cudaFree(h->d_has_prev);
   cudaFree(h->d_u_guess);
   cudaFree(h->d_kk);
+  cudaFree(h->d_guess);
+  cudaFree(h->d_u_split);
   cudaFree(h->d_queue);
   cudaFree(h->d_warp_cycles);
   cudaFree(h->d_iter_log);

@@ -30,6 +30,9 @@ struct cpmpc_plant_solver {
   unsigned char* d_has_prev = nullptr;
   double* d_u_guess = nullptr;
   double* d_kk = nullptr;
+  bool split = false;         // serial rollouts in their own one-thread-per-instance kernels (large batches)
+  double* d_guess = nullptr;  // [B, NX NS]
+  double* d_u_split = nullptr;
   unsigned long long* d_queue = nullptr;
   double* d_iter_log = nullptr;
   bool log_enabled = false;
@@ -122,8 +125,26 @@ int Launch(cpmpc_plant_solver* h, gp::GpIO io, cudaStream_t stream) {
   io.kk_scratch = h->d_kk;
   io.queue = h->d_queue;
   io.iter_log = h->log_enabled ? h->d_iter_log : nullptr;
+  if (!h->split) {
+    fn<<<h->grid, 32 * h->warps_per_block, h->smem_bytes, stream>>>(h->cfg, io);
+    cpmpc::detail::CountLaunches(1);
+    CPMPC_CUDA_TRY(cudaGetLastError());
+    return CPMPC_OK;
+  }
+  // Split launch (large batches): guess rollouts -> SQP -> predicted states, the rollouts one thread per instance
+  if (io.u_out == nullptr) io.u_out = h->d_u_split;
+  io.guess = h->d_guess;
+  io.split = 1;
+  const unsigned wide_blocks = static_cast<unsigned>((h->B + 127) / 128);
+  const bool single = h->plant == CPMPC_PLANT_SINGLE;
+  if (single) gp::plant_guess_kernel<gp::SinglePlant><<<wide_blocks, 128, 0, stream>>>(h->cfg, io, h->d_guess);
+  else gp::plant_guess_kernel<gp::DoublePlant><<<wide_blocks, 128, 0, stream>>>(h->cfg, io, h->d_guess);
   fn<<<h->grid, 32 * h->warps_per_block, h->smem_bytes, stream>>>(h->cfg, io);
-  cpmpc::detail::CountLaunches(1);
+  if (io.pred_out != nullptr) {
+    if (single) gp::plant_post_kernel<gp::SinglePlant><<<wide_blocks, 128, 0, stream>>>(h->cfg, io, io.u_out);
+    else gp::plant_post_kernel<gp::DoublePlant><<<wide_blocks, 128, 0, stream>>>(h->cfg, io, io.u_out);
+  }
+  cpmpc::detail::CountLaunches(io.pred_out != nullptr ? 3 : 2);
   CPMPC_CUDA_TRY(cudaGetLastError());
   return CPMPC_OK;
 }
@@ -299,6 +320,13 @@ int cpmpc_plant_create(int plant, const cpmpc_plant_params* params, int64_t batc
   CPMPC_CUDA_TRY(cudaMemset(h->d_has_prev, 0, batch));
   CPMPC_CUDA_TRY(cudaMemset(h->d_prev, 0, sizeof(double) * batch * k.N));
   CPMPC_CUDA_TRY(cudaMalloc(&h->d_kk, sizeof(double) * n_groups * k.kk_stride));
+  // split launch from two waves of the persistent grid, as in cpmpc_create_ex; results do not depend on it
+  h->split = batch >= 2 * n_groups;
+  if (const char* env = std::getenv("CPMPC_SPLIT")) h->split = std::atoi(env) != 0;
+  if (h->split) {
+    CPMPC_CUDA_TRY(cudaMalloc(&h->d_guess, sizeof(double) * batch * h->nx * k.NS));
+    CPMPC_CUDA_TRY(cudaMalloc(&h->d_u_split, sizeof(double) * batch * k.W));
+  }
   CPMPC_CUDA_TRY(cudaMalloc(&h->d_queue, sizeof(unsigned long long) * 2));
   CPMPC_CUDA_TRY(cudaMemset(h->d_queue, 0, sizeof(unsigned long long) * 2));
   CPMPC_CUDA_TRY(cudaMalloc(&h->d_u_guess, sizeof(double) * k.W));
@@ -320,6 +348,8 @@ int cpmpc_plant_destroy(cpmpc_plant_handle h) {
   cudaFree(h->d_has_prev);
   cudaFree(h->d_u_guess);
   cudaFree(h->d_kk);
+  cudaFree(h->d_guess);
+  cudaFree(h->d_u_split);
   cudaFree(h->d_queue);
   cudaFree(h->d_iter_log);
   cudaFree(h->d_states);

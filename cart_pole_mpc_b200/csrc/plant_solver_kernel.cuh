@@ -243,6 +243,9 @@ struct GpIO {
   double* iter_log;          // [B,max_iter,27] or nullptr
   double* kk_scratch;        // [n_groups, kk_stride]
   unsigned long long* queue; // [2]
+  // split launch (cpmpc_plant_capi.cu Launch), as in solver_kernel.cuh: the serial rollouts in their own kernels
+  const double* guess;       // [B, NX NS] shooting states of the initial guess, or nullptr: integrate them here
+  int split;                 // 1: the predicted states are plant_post_kernel's
 };
 
 enum : int { SR_SUCCESS = 0, SR_MAX_ITERATIONS = 1, SR_FIRST_ORDER = 2, SR_POSITIVE_DERIVATIVE = 3,
@@ -1594,7 +1597,11 @@ __global__ void __launch_bounds__(256, 1) plant_solve_kernel(const GpCfg cfg, co
       #pragma unroll 1
       for (int q = c.gl; q < W; q += L) u[q] = warm ? prev[NX * NS + ((q + 1 < W) ? q + 1 : q)] : io.u_guess[q];
       GP_GSYNC();
-      if (c.gl == 0) {
+      if (io.guess != nullptr) {
+        const double* gx = io.guess + inst * (NX * NS);
+        #pragma unroll 1
+        for (int q = c.gl; q < NX * NS; q += L) xs[q] = gx[q];
+      } else if (c.gl == 0) {
         // FillInitialGuess (optimization.cc:333-351)
         typename PL::Const Pl;
         PL::load(Pl, c.sm + cfg.off_dyn);
@@ -1637,7 +1644,7 @@ __global__ void __launch_bounds__(256, 1) plant_solve_kernel(const GpCfg cfg, co
       }
       if (c.gl == 0) {
         io.has_prev[inst] = 1;
-        if (io.pred_out != nullptr) {
+        if (io.pred_out != nullptr && !io.split) {
           // ComputePredictedStates (optimization.cc:353-371)
           typename PL::Const Pl;
           PL::load(Pl, c.sm + cfg.off_dyn);
@@ -1679,6 +1686,80 @@ __global__ void __launch_bounds__(256, 1) plant_solve_kernel(const GpCfg cfg, co
     if (atomicAdd(io.queue + 1, 1ull) == total - 1) {
       io.queue[0] = 0ull;
       io.queue[1] = 0ull;
+    }
+  }
+}
+
+// The plant constants exactly as a lane of plant_solve_kernel sees them: every one a finished double that went through
+// shared memory.  Without the barrier the compiler may contract a multiplication inside PL::make with an addition of the
+// dynamics into one FMA, and the rollouts of the split launch would round differently from the fused kernel's.
+template <class PL>
+__device__ __forceinline__ typename PL::Const make_plant_const_opaque(const double* __restrict__ p) {
+  double tmp[PL::NC];
+  PL::store(tmp, PL::make(p));
+#pragma unroll
+  for (int i = 0; i < PL::NC; ++i) asm volatile("" : "+d"(tmp[i]));
+  typename PL::Const c;
+  PL::load(c, tmp);
+  return c;
+}
+
+// Split launch: FillInitialGuess (optimization.cc:333-351) and ComputePredictedStates (optimization.cc:353-371) with one
+// THREAD per instance, before and after plant_solve_kernel (see cpmpc_guess_kernel / cpmpc_post_kernel in
+// solver_kernel.cuh).  Same controls, same rk4_step, same order: bit-identical to the fused path.
+template <class PL>
+__global__ void __launch_bounds__(128) plant_guess_kernel(const GpCfg cfg, const GpIO io, double* __restrict__ guess) {
+  constexpr int NX = PL::NX;
+  const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= io.B) return;
+  const int W = cfg.W, S = cfg.S, NS = cfg.NS, N = cfg.N;
+  const typename PL::Const P = make_plant_const_opaque<PL>(io.dyn + inst * PL::NP);
+  const double* ps = io.states + inst * NX;
+  double x[NX];
+  double* gx = guess + inst * (NX * NS);
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+    x[i] = ps[i];
+    gx[i] = x[i];
+  }
+  const bool warm = io.has_prev[inst] != 0;
+  const double* pu = warm ? io.prev + inst * N + NX * NS : io.u_guess;
+  #pragma unroll 1
+  for (int s = 1; s < NS; ++s) {
+    #pragma unroll 1
+    for (int i = 0; i < S; ++i) {
+      const int q = (s - 1) * S + i;
+      const double uq = warm ? pu[(q + 1 < W) ? q + 1 : q] : pu[q];
+      rk4_step<PL>(P, x, uq, cfg.dt);
+#pragma unroll
+      for (int a = 0; a < NX; ++a)
+        if (PL::is_angle(a)) x[a] = mod_pi(x[a]);
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) gx[NX * s + i] = x[i];
+  }
+}
+
+template <class PL>
+__global__ void __launch_bounds__(128) plant_post_kernel(const GpCfg cfg, const GpIO io, const double* __restrict__ u) {
+  constexpr int NX = PL::NX;
+  const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= io.B || io.pred_out == nullptr) return;
+  const int W = cfg.W;
+  const typename PL::Const P = make_plant_const_opaque<PL>(io.dyn + inst * PL::NP);
+  const double* ps = io.states + inst * NX;
+  double x[NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) x[i] = ps[i];
+  const double* pu = u + inst * W;
+  double* po = io.pred_out + (size_t)inst * W * NX;
+  #pragma unroll 1
+  for (int q = 0; q < W; ++q) {
+    rk4_step<PL>(P, x, pu[q], cfg.dt);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      if (PL::is_angle(i)) x[i] = mod_pi(x[i]);
+      po[NX * q + i] = x[i];
     }
   }
 }

@@ -94,6 +94,13 @@ struct KernelIO {
   // warp of a launch and, when a launch is one wave, the instances it carried and where its time went
   // (bench.py per_rank, profiles/shard_times.py)
   unsigned long long* warp_cycles;
+  // Split launch (large batches, cpmpc_capi.cu Launch): the two serial rollouts of a Step - FillInitialGuess before the
+  // solve, ComputePredictedStates (and the plant step of the closed loop) after it - run in their own kernels with one
+  // THREAD per instance (cpmpc_guess_kernel / cpmpc_post_kernel) instead of on one lane of every group in here.
+  const double* guess;       // [B, 4 NS] shooting states of the initial guess, or nullptr: integrate them here
+  int split;                 // 1: predicted states, plant step and controls_out are cpmpc_post_kernel's
+  long long step_index;      // closed loop through split launches: the control tick this launch belongs to ...
+  long long n_steps_total;   // ... of this many (row length of controls_out)
 };
 
 // mini_opt enums (dependencies/mini_opt/include/mini_opt/structs.hpp:159-248), by declaration order.
@@ -1541,7 +1548,12 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
           u[q] = warm ? prev[4 * NS + ((q + 1 < W) ? q + 1 : q)] : io.u_guess[q];
         }
         CPMPC_GSYNC();
-        if (c.gl == 0) {
+        if (io.guess != nullptr) {
+          // split launch: cpmpc_guess_kernel has integrated the shooting states already
+          const double* gx = io.guess + inst * (4 * NS);
+          #pragma unroll 1
+          for (int q = c.gl; q < 4 * NS; q += L) xs[q] = gx[q];
+        } else if (c.gl == 0) {
           // FillInitialGuess: all shooting states re-integrated from x(0) (optimization.cc:333-351); the states at
           // the chunk boundaries inside a segment are kept for the first linearisation
           DynConst Pl;
@@ -1602,7 +1614,7 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
         }
         if (c.gl == 0) {
           if (keep) io.has_prev[inst] = 1;
-          if (io.pred_out != nullptr) {
+          if (io.pred_out != nullptr && !io.split) {
             // ComputePredictedStates (optimization.cc:353-371)
             DynConst Pl;
             load_dyn_const(Pl, c.sm + cfg.off_dyn);
@@ -1639,7 +1651,7 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
                       res.termination == TS_REJECTED)
                          ? 1
                          : 0;
-          if (io.sim) {
+          if (io.sim && !io.split) {
             // Simulator::Step(control_dt, u[0]) with 1 ms sub-steps (simulator.cc:11-36)
             const double u0 = u[0];
             if (io.controls_out != nullptr) io.controls_out[inst * io.n_steps + step] = u0;
@@ -1658,7 +1670,7 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
             for (int i = 0; i < 4; ++i) x_cur[i] = x[i];
           }
         }
-        if (io.sim) {
+        if (io.sim && !io.split) {
           const int src = (c.gmask == 0xffffffffu) ? 0 : (__ffs(c.gmask) - 1);
 #pragma unroll
           for (int i = 0; i < 4; ++i) x_cur[i] = __shfl_sync(c.gmask, x_cur[i], src);
@@ -1672,7 +1684,7 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
       }
     }
     if (have && c.gl == 0) {
-      if (io.sim) {
+      if (io.sim && !io.split) {
         double* ps = io.states_io + inst * CPMPC_STATE_STRIDE;
 #pragma unroll
         for (int i = 0; i < 4; ++i) ps[i] = x_cur[i];
@@ -1705,6 +1717,96 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
 
 #undef CPMPC_GSYNC
 #undef CPMPC_PARK
+
+// The plant constants exactly as a lane of cpmpc_solve_kernel sees them: every one a finished double that went through
+// shared memory.  Without the barrier the compiler may contract a multiplication inside make_dyn_const with an addition
+// of the dynamics into one FMA, and the rollouts of the split launch would round differently from the fused kernel's.
+__device__ __forceinline__ DynConst make_dyn_const_opaque(const double* __restrict__ p) {
+  double tmp[DYN_CONST_DOUBLES];
+  store_dyn_const(tmp, make_dyn_const(p));
+#pragma unroll
+  for (int i = 0; i < DYN_CONST_DOUBLES; ++i) asm volatile("" : "+d"(tmp[i]));
+  DynConst c;
+  load_dyn_const(c, tmp);
+  return c;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Split launch, kernel 1 of 3: FillInitialGuess (optimization.cc:333-351) for every instance of the batch, one THREAD
+// per instance.  Inside cpmpc_solve_kernel this 40-knot serial rollout occupies one lane of each group (a quarter of a
+// warp at the defaults, an eighth at W = 160) while the others wait; here every lane integrates its own plant.  Same
+// controls (warm start shifted by one knot, optimization.cc:57-61, or the cold-start guess), same rk4_step, same order:
+// the shooting states are bit-identical to the fused path's (profiles/ab_compare.py).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) cpmpc_guess_kernel(const KernelCfg cfg, const KernelIO io, double* __restrict__ guess) {
+  const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= io.B) return;
+  const int W = cfg.W, S = cfg.S, NS = cfg.NS, N = cfg.N;
+  const DynConst P = make_dyn_const_opaque(io.dyn + inst * CPMPC_DYN_STRIDE);
+  const double* ps = (io.sim ? io.states_io : io.states) + inst * CPMPC_STATE_STRIDE;
+  double x[4] = {ps[0], ps[1], ps[2], ps[3]};
+  const bool warm = io.has_prev[inst] != 0;
+  const double* pu = warm ? io.prev + inst * N + 4 * NS : io.u_guess;
+  double* gx = guess + inst * (4 * NS);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) gx[i] = x[i];
+  #pragma unroll 1
+  for (int s = 1; s < NS; ++s) {
+    #pragma unroll 1
+    for (int i = 0; i < S; ++i) {
+      const int q = (s - 1) * S + i;
+      const double uq = warm ? pu[(q + 1 < W) ? q + 1 : q] : pu[q];
+      rk4_step<false>(P, x, uq, cfg.dt);
+      x[1] = mod_pi(x[1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gx[4 * s + i] = x[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Split launch, kernel 3 of 3: ComputePredictedStates (optimization.cc:353-371) and, in the closed loop, the plant's
+// Simulator::Step(control_dt, u[0]) with 1 ms sub-steps (simulator.cc:11-36), one THREAD per instance, from the controls
+// the solve kernel left in u[B, W].
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) cpmpc_post_kernel(const KernelCfg cfg, const KernelIO io, const double* __restrict__ u) {
+  const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= io.B) return;
+  const int W = cfg.W;
+  const DynConst P = make_dyn_const_opaque(io.dyn + inst * CPMPC_DYN_STRIDE);
+  const double* ps = (io.sim ? io.states_io : io.states) + inst * CPMPC_STATE_STRIDE;
+  const double x0[4] = {ps[0], ps[1], ps[2], ps[3]};
+  const double* pu = u + inst * W;
+  if (io.pred_out != nullptr) {
+    double x[4] = {x0[0], x0[1], x0[2], x0[3]};
+    double* po = io.pred_out + (size_t)inst * W * 4;
+    #pragma unroll 1
+    for (int q = 0; q < W; ++q) {
+      rk4_step<false>(P, x, pu[q], cfg.dt);
+      x[1] = mod_pi(x[1]);
+      po[4 * q] = x[0];
+      po[4 * q + 1] = x[1];
+      po[4 * q + 2] = x[2];
+      po[4 * q + 3] = x[3];
+    }
+  }
+  if (io.sim) {
+    const double u0 = pu[0];
+    if (io.controls_out != nullptr) io.controls_out[inst * io.n_steps_total + io.step_index] = u0;
+    double dt = cfg.dt;
+    double x[4] = {x0[0], x0[1], x0[2], x0[3]};
+    if (isfinite(u0)) {
+      while (dt > 0.0) {
+        rk4_step<false>(P, x, u0, fmin(dt, 0.001));
+        x[1] = mod_pi(x[1]);
+        dt -= 0.001;
+      }
+    }
+    double* pw = io.states_io + inst * CPMPC_STATE_STRIDE;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pw[i] = x[i];
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Batched plant simulator: Simulator::Step (optimization/simulator.cc:11-36), one thread per plant.

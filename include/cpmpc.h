@@ -107,6 +107,17 @@ int cpmpc_create(const cpmpc_params* params, int64_t batch, int device, cpmpc_ha
  *                           0.50 ms with LOW_LATENCY and 0.61 ms with the default mapping); large batches lose most
  *                           of their throughput.  Same rounding caveat as LOW_LATENCY.  Takes precedence over it. */
 #define CPMPC_FLAG_MIN_LATENCY 2u
+/*   CPMPC_FLAG_SPLIT_LAUNCH / CPMPC_FLAG_FUSED_LAUNCH  how a Step is launched; the results are bit-identical either
+ *                           way.  Fused: one kernel per call (per closed loop), the two serial rollouts of a Step -
+ *                           FillInitialGuess and ComputePredictedStates, optimization.cc:333-371 - on one lane of each
+ *                           instance's lane group.  Split: those rollouts (and the closed loop's plant step) run in
+ *                           their own kernels with one thread per instance before and after the solve kernel, three
+ *                           stream-ordered launches per control tick: 9 % more solves/s at 65536 instances, 12 % at
+ *                           W = 160, nothing to gain while the batch is a single wave.  Without either flag the
+ *                           library picks by batch size (split from two waves of the persistent grid, five in the
+ *                           closed loop).  Ignored (fused) under LOW_LATENCY / MIN_LATENCY. */
+#define CPMPC_FLAG_SPLIT_LAUNCH 4u
+#define CPMPC_FLAG_FUSED_LAUNCH 8u
 int cpmpc_create_ex(const cpmpc_params* params, int64_t batch, int device, uint32_t flags, cpmpc_handle* out);
 int cpmpc_destroy(cpmpc_handle h);
 

@@ -320,3 +320,35 @@ def test_double_pendulum_against_reference_solver(oracle, over, min_frac):
     ref2 = oracle.dp_ref_batch_step(oracle.dp_opt_array(**over), st, dy, sp, prev=ref.solution,
                                     has_prev=np.ones(B, np.uint8), want_iter_log=False)
     _check(out2, ref2, min_frac=0.93, min_iter=0.97)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("plant", ["double", "single"])
+def test_plant_split_launch_equals_fused_launch(plant, monkeypatch):
+    """The plant-generic kernel's split launch (guess / solve / predicted-state kernels, csrc/cpmpc_plant_capi.cu Launch;
+    picked by batch size, forced here through the experiment switch): the same bits as the fused kernel for a cold
+    and a warm-started step, with and without predicted states, on a ragged batch."""
+    from cart_pole_mpc_b200 import synthetic
+    from cart_pole_mpc_b200.plant import PlantBatchedOptimization
+    B = 77
+    if plant == "double":
+        st, dy, sp = synthetic.double_swingup_batch(B)
+    else:
+        st, dy, sp = synthetic.swingup_batch(B)
+    outs = []
+    for split in ("0", "1"):
+        monkeypatch.setenv("CPMPC_SPLIT", split)
+        s = PlantBatchedOptimization(plant, B, device=0)
+        cold = s.step(st, dy, sp)
+        warm = s.step(st + 0.01, dy, sp)
+        nopred = s.step(st + 0.02, dy, sp, want_predicted=False)
+        prev, has = s.get_previous_solution()
+        outs.append((cold, warm, nopred, prev, has))
+        s.close()
+    a, b = outs
+    for k in range(3):
+        assert np.array_equal(a[k].u, b[k].u, equal_nan=True), k
+        assert a[k].stats.tobytes() == b[k].stats.tobytes(), k
+        if k < 2:
+            assert np.array_equal(a[k].predicted_states, b[k].predicted_states, equal_nan=True), k
+    assert np.array_equal(a[3], b[3], equal_nan=True) and np.array_equal(a[4], b[4])

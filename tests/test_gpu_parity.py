@@ -819,3 +819,34 @@ def test_pipelined_steps_equal_synchronous_steps():
     ref2 = _solver(B)
     ref2.step(states[2], dy, sp)
     assert np.array_equal(nxt.u, ref2.step(states[3], dy, sp).u)
+
+
+@pytest.mark.parametrize("over", [dict(), dict(window_length=160), dict(state_spacing=5, max_iterations=10)],
+                         ids=["defaults", "w160", "s5"])
+def test_split_launch_equals_fused_launch(over):
+    """CPMPC_FLAG_SPLIT_LAUNCH (guess / solve / predicted-state kernels, the serial rollouts of
+    optimization.cc:333-371 one thread per instance) against CPMPC_FLAG_FUSED_LAUNCH: the same bits for a cold step, a
+    warm-started step with per-instance weights, a step without predicted states, and the closed loop (which asks for
+    no u_out: the library's own control scratch), on a ragged batch."""
+    from cart_pole_mpc_b200 import BatchedOptimization, synthetic
+    B = 203
+    st, dy, sp, wt = synthetic.sweep_batch(B)
+    outs = []
+    for split in (False, True):
+        s = BatchedOptimization(B, device=0, split_launch=split, **over)
+        cold = s.step(st, dy, sp)
+        warm = s.step(st + 0.01, dy, sp, weights=wt)
+        nopred = s.step(st + 0.02, dy, sp, want_predicted=False)
+        prev, has = s.get_previous_solution()
+        s.reset()
+        fin, ctl, counts = s.closed_loop(4, st, dy, sp)
+        outs.append((cold, warm, nopred, prev, has, fin, ctl, counts))
+        s.close()
+    a, b = outs
+    for k in range(3):
+        assert np.array_equal(a[k].u, b[k].u, equal_nan=True), k
+        assert a[k].stats.tobytes() == b[k].stats.tobytes(), k
+        if k < 2:
+            assert np.array_equal(a[k].predicted_states, b[k].predicted_states, equal_nan=True), k
+    for k in range(3, 8):
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
