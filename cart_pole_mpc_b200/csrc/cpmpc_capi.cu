@@ -148,8 +148,9 @@ void BuildLayout(KernelCfg& k) {
   k.off_xkc = k.off_uc + W;
   // QP scratch: the condensed form's Z [4][W] and tinv [W]; the Riccati recursion only stages the feedback rows
   // of ONE segment here for its forward sweep (its value function lives in registers)
-  const int n_ric = S * GAIN_STRIDE;
-  const int n_cond = k.condensed ? 5 * W : 0;
+  if (k.stage_knots < 1 || k.stage_knots > S) k.stage_knots = S;
+  const int n_ric = k.stage_knots * GAIN_STRIDE;
+  const int n_cond = k.condensed ? (k.z_global ? W : 5 * W) : 0;
   k.off_aug = take(n_ric > n_cond ? n_ric : n_cond);
   k.off_dyn = take(DYN_CONST_DOUBLES);
   // odd stride (in doubles) so that the same field of neighbouring instances falls into different banks
@@ -470,6 +471,8 @@ int cpmpc_create_ex(const cpmpc_params* params, int64_t batch, int device, uint3
     if (std::strcmp(env, "riccati") == 0) k.condensed = 0;
     if (std::strcmp(env, "condensed") == 0) k.condensed = 1;
   }
+  k.z_global = 0;
+  k.stage_knots = k.S;
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   const bool chunked = lanes > base_lanes;
@@ -504,8 +507,43 @@ int cpmpc_create_ex(const cpmpc_params* params, int64_t batch, int device, uint3
     const int v = std::atoi(env);
     if (v >= 1 && v <= 8) wpb_max = v;
   }
+  const int wpb_cap = wpb_max;
   while (wpb_max > 1 && smem_per_warp * wpb_max > static_cast<size_t>(prop.sharedMemPerBlockOptin)) --wpb_max;
   const long long warps_needed = (batch + groups_per_warp - 1) / groups_per_warp;
+  // Compact layout for batches that do not fit one wave of the roomy one: the condensed QP's Z rows move from shared
+  // memory to the group's L2-resident global scratch (the Riccati recursion's, never live in the same iteration) and
+  // the Riccati forward sweep stages fewer knots at a time, until a warp more fits on the SM (defaults: 573 -> 437
+  // doubles per instance, 6 -> 8 warps per SM, two per scheduler).  The arithmetic does not change: same bits.  At
+  // equal warps per SM global Z rows cost 5 % (L2 round trips inside the substitutions), so a batch that fits one wave
+  // anyway keeps them in shared memory (4096 instances: 0.704 against 0.745 ms); eight warps instead of six are worth
+  // 11 % at 65536 instances (profiles/r02_w_layout_sweep.jsonl).
+  const char* env_z = std::getenv("CPMPC_ZGLOBAL");
+  const char* env_sk = std::getenv("CPMPC_STAGE_KNOTS");
+  const bool want_compact = env_z != nullptr ? std::atoi(env_z) != 0
+                                             : warps_needed > static_cast<long long>(wpb_max) * prop.multiProcessorCount;
+  if (want_compact && k.condensed && wpb_max < wpb_cap) {
+    KernelCfg best = k;
+    int best_wpb = wpb_max;
+    for (int sk = k.S; sk >= 1; --sk) {
+      KernelCfg t = k;
+      t.z_global = 1;
+      t.stage_knots = env_sk != nullptr ? std::atoi(env_sk) : sk;
+      BuildLayout(t);
+      const size_t per_warp = sizeof(double) * static_cast<size_t>(t.stride) * groups_per_warp;
+      int w = wpb_cap;
+      while (w > 1 && per_warp * w > static_cast<size_t>(prop.sharedMemPerBlockOptin)) --w;
+      if (w > best_wpb) {
+        best = t;
+        best_wpb = w;
+      }
+      if (best_wpb == wpb_cap || env_sk != nullptr) break;
+    }
+    if (best_wpb > wpb_max || env_z != nullptr) {
+      k = best;
+      wpb_max = best_wpb;
+      smem_per_warp = sizeof(double) * static_cast<size_t>(k.stride) * groups_per_warp;
+    }
+  }
   int wpb = wpb_max;
   if (warps_needed <= static_cast<long long>(wpb_max) * prop.multiProcessorCount) {
     wpb = static_cast<int>((warps_needed + prop.multiProcessorCount - 1) / prop.multiProcessorCount);

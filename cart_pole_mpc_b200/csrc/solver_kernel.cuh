@@ -49,6 +49,8 @@ constexpr int NCOL_MAX = XI_DIM + NR_MAX;
 struct KernelCfg {
   int W, S, NS, nseg, N, max_iter, max_ls;
   int condensed;  // 1: lambda == 0 iterations use the condensed QP (short horizons), 0: always Riccati
+  int z_global;   // 1: the condensed QP's Z rows live in the global scratch instead of shared memory
+  int stage_knots;  // knots of Riccati feedback rows staged in shared memory at a time (S, or fewer to save shared memory)
   int cps;     // chunks per shooting segment in the linearisation
   int nchunk;  // nseg * cps
   int stride;  // doubles of shared memory per instance
@@ -541,11 +543,13 @@ __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights& w, const
     dxs[2] = m0[2];
     dxs[3] = m0[3];
   }
-  // rows of a segment: S * GAIN_STRIDE doubles, NPF per lane (prefetched into registers one segment ahead, so the L2
-  // round trip of segment s + 1 overlaps the first lane's work on segment s)
+  // rows of a segment: S * GAIN_STRIDE doubles, staged k.stage_knots knots at a time (a whole segment unless shared
+  // memory is short); when a whole segment fits NPF per lane it is prefetched into registers one segment ahead, so the L2
+  // round trip of segment s + 1 overlaps the first lane's work on segment s
   constexpr int NPF = 4;
   const int n_rows = S * GAIN_STRIDE;
-  const bool fits = n_rows <= NPF * L;
+  const int SK = k.stage_knots;
+  const bool fits = n_rows <= NPF * L && SK == S;
   double pf[NPF];
   auto fetch = [&](const int seg) {
     const double* src = c.kk + (size_t)seg * n_rows;
@@ -558,49 +562,58 @@ __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights& w, const
   CPMPC_GSYNC();  // the backward sweep's stores are visible to the group
   if (fits) fetch(0);
   for (int s = 0; s < nseg; ++s) {
-    if (fits) {
+    #pragma unroll 1
+    for (int i0 = 0; i0 < S; i0 += SK) {
+      const int i1 = (i0 + SK < S) ? i0 + SK : S;
+      if (fits) {
 #pragma unroll
-      for (int q = 0; q < NPF; ++q) {
-        const int t = c.gl + q * L;
-        if (t < n_rows) stage[t] = pf[q];
+        for (int q = 0; q < NPF; ++q) {
+          const int t = c.gl + q * L;
+          if (t < n_rows) stage[t] = pf[q];
+        }
+        if (s + 1 < nseg) fetch(s + 1);
+      } else {
+        const double* src = c.kk + (size_t)s * n_rows + i0 * GAIN_STRIDE;
+        const int nb = (i1 - i0) * GAIN_STRIDE;
+        for (int t = c.gl; t < nb; t += L) stage[t] = __ldcg(src + t);
       }
-      if (s + 1 < nseg) fetch(s + 1);
-    } else {
-      const double* src = c.kk + (size_t)s * n_rows;
-      for (int t = c.gl; t < n_rows; t += L) stage[t] = __ldcg(src + t);
-    }
-    CPMPC_GSYNC();
-    if (c.gl == 0) {
-      const double* Ph = Phi + 16 * s;
-      const double n0 = Ph[0] * y0 + Ph[1] * y1 + Ph[2] * y2 + Ph[3] * y3 + ev[4 * s];
-      const double n1 = Ph[4] * y0 + Ph[5] * y1 + Ph[6] * y2 + Ph[7] * y3 + ev[4 * s + 1];
-      const double n2 = Ph[8] * y0 + Ph[9] * y1 + Ph[10] * y2 + Ph[11] * y3 + ev[4 * s + 2];
-      const double n3 = Ph[12] * y0 + Ph[13] * y1 + Ph[14] * y2 + Ph[15] * y3 + ev[4 * s + 3];
-      y0 = n0;
-      y1 = n1;
-      y2 = n2;
-      y3 = n3;
-      for (int i = 0; i < S; ++i) {
-        const int col = s * S + i;
-        const double* g = stage + i * GAIN_STRIDE;
-        double acc = g[0] * y0 + g[1] * y1 + g[2] * y2 + g[3] * y3 + g[4] * pv;
-        double acc2 = g[XI_DIM] * coef[0] + g[XI_DIM + 1] * coef[1] + g[XI_DIM + 2] * coef[2] + g[XI_DIM + 3] * coef[3] +
-                      g[XI_DIM + 4] * coef[4];
-        const double v = -(acc + acc2);
-        cdx = fma(du[col], v, cdx);  // du[] still holds c_u
-        du[col] = v;
-        y0 = fma(Gam[col], v, y0);
-        y1 = fma(Gam[W + col], v, y1);
-        y2 = fma(Gam[2 * W + col], v, y2);
-        y3 = fma(Gam[3 * W + col], v, y3);
-        pv = v;
+      CPMPC_GSYNC();
+      if (c.gl == 0) {
+        if (i0 == 0) {
+          const double* Ph = Phi + 16 * s;
+          const double n0 = Ph[0] * y0 + Ph[1] * y1 + Ph[2] * y2 + Ph[3] * y3 + ev[4 * s];
+          const double n1 = Ph[4] * y0 + Ph[5] * y1 + Ph[6] * y2 + Ph[7] * y3 + ev[4 * s + 1];
+          const double n2 = Ph[8] * y0 + Ph[9] * y1 + Ph[10] * y2 + Ph[11] * y3 + ev[4 * s + 2];
+          const double n3 = Ph[12] * y0 + Ph[13] * y1 + Ph[14] * y2 + Ph[15] * y3 + ev[4 * s + 3];
+          y0 = n0;
+          y1 = n1;
+          y2 = n2;
+          y3 = n3;
+        }
+        for (int i = i0; i < i1; ++i) {
+          const int col = s * S + i;
+          const double* g = stage + (i - i0) * GAIN_STRIDE;
+          double acc = g[0] * y0 + g[1] * y1 + g[2] * y2 + g[3] * y3 + g[4] * pv;
+          double acc2 = g[XI_DIM] * coef[0] + g[XI_DIM + 1] * coef[1] + g[XI_DIM + 2] * coef[2] + g[XI_DIM + 3] * coef[3] +
+                        g[XI_DIM + 4] * coef[4];
+          const double v = -(acc + acc2);
+          cdx = fma(du[col], v, cdx);  // du[] still holds c_u
+          du[col] = v;
+          y0 = fma(Gam[col], v, y0);
+          y1 = fma(Gam[W + col], v, y1);
+          y2 = fma(Gam[2 * W + col], v, y2);
+          y3 = fma(Gam[3 * W + col], v, y3);
+          pv = v;
+        }
+        if (i1 == S) {
+          dxs[4 * (s + 1)] = y0;
+          dxs[4 * (s + 1) + 1] = y1;
+          dxs[4 * (s + 1) + 2] = y2;
+          dxs[4 * (s + 1) + 3] = y3;
+        }
       }
-      dxs[4 * (s + 1)] = y0;
-      dxs[4 * (s + 1) + 1] = y1;
-      dxs[4 * (s + 1) + 2] = y2;
-      dxs[4 * (s + 1) + 3] = y3;
+      CPMPC_GSYNC();  // the staged rows have been consumed
     }
-    CPMPC_GSYNC();  // the rows of this segment have been consumed
   }
   return true;
 }
@@ -627,8 +640,10 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, boo
   const double* Phi = c.sm + k.off_phi;
   const double* ev = c.sm + k.off_e;
   const double* Gam = c.sm + k.off_gam;
-  double* Z = c.sm + k.off_aug;  // [4][W]
-  double* tinv = Z + 4 * W;      // reciprocal pivots of T = L D L^T
+  // Z [4][W] in shared memory behind tinv, or (k.z_global) in the group's L2-resident global scratch, which the Riccati
+  // recursion - never active in the same iteration - uses for its feedback rows
+  double* tinv = c.sm + k.off_aug;  // reciprocal pivots of T = L D L^T
+  double* Z = k.z_global ? c.kk : tinv + W;
   // sub-diagonal multipliers of the unit bidiagonal factor: l_j = -w_r^2 / d_{j-1}, recomputed from the pivots where they
   // are used (one multiply off the dependent chain) instead of being stored: W doubles less shared memory per instance,
   // which is what lets a sixth warp fit on an SM at the default problem size

@@ -850,3 +850,32 @@ def test_split_launch_equals_fused_launch(over):
             assert np.array_equal(a[k].predicted_states, b[k].predicted_states, equal_nan=True), k
     for k in range(3, 8):
         assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
+@pytest.mark.parametrize("over", [dict(), dict(state_spacing=5, max_iterations=10), dict(u_cost_weight=0.0)],
+                         ids=["defaults", "s5", "lm_heavy"])
+def test_compact_shared_memory_layout_equals_roomy_layout(over, monkeypatch):
+    """Batches beyond one wave use a compact shared-memory layout (csrc/cpmpc_capi.cu: the condensed QP's Z rows in the
+    L2-resident global scratch, the Riccati forward sweep staged a few knots at a time) so that eight warps fit on an
+    SM.  Forced here on a small batch through the experiment switches: the same bits as the roomy layout, including
+    instances that take Levenberg-Marquardt iterations through the Riccati recursion (u_cost_weight = 0)."""
+    from cart_pole_mpc_b200 import BatchedOptimization, synthetic
+    B = 333
+    st, dy, sp = synthetic.swingup_batch(B, seed=13)
+    outs = []
+    for env in (dict(CPMPC_ZGLOBAL="0"), dict(CPMPC_ZGLOBAL="1"), dict(CPMPC_ZGLOBAL="1", CPMPC_STAGE_KNOTS="3")):
+        monkeypatch.delenv("CPMPC_STAGE_KNOTS", raising=False)
+        for key, val in env.items():
+            monkeypatch.setenv(key, val)
+        s = BatchedOptimization(B, device=0, **over)
+        cold = s.step(st, dy, sp)
+        warm = s.step(st + 0.01, dy, sp)
+        outs.append((cold, warm))
+        s.close()
+    for other in outs[1:]:
+        for k in range(2):
+            assert np.array_equal(outs[0][k].u, other[k].u, equal_nan=True), k
+            assert np.array_equal(outs[0][k].predicted_states, other[k].predicted_states, equal_nan=True), k
+            assert outs[0][k].stats.tobytes() == other[k].stats.tobytes(), k
+    if over.get("u_cost_weight") == 0.0:
+        assert (outs[0][0].stats["lambda"] > 0).any() or (outs[0][0].stats["n_failed_line_searches"] > 0).any()
