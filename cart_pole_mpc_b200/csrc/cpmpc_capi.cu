@@ -575,13 +575,12 @@ int cpmpc_create_ex(const cpmpc_params* params, int64_t batch, int device, uint3
   CUDA_TRY(cudaMalloc(&h->d_kk, sizeof(double) * n_groups * k.kk_stride));
   CUDA_TRY(cudaMalloc(&h->d_warp_cycles, sizeof(unsigned long long) * WARP_REC * h->grid * wpb));
   CUDA_TRY(cudaMemset(h->d_warp_cycles, 0, sizeof(unsigned long long) * WARP_REC * h->grid * wpb));
-  // Large batches run the serial rollouts of a Step in their own one-thread-per-instance kernels (Launch).  "Large" =
-  // more instances than two full waves of the persistent grid: below that the step is the latency of ONE solve and
-  // two extra launches only add to it.  Results do not depend on the choice.
-  // The closed loop gains less (its fused form has no tail per control tick: warps run on into the next tick) and
-  // breaks even at about four waves (profiles/r02_v_ab_split.jsonl).
-  h->split = batch >= 2 * n_groups;
-  h->split_loop = batch >= 5 * n_groups;
+  // Batches beyond one wave of the persistent grid run the serial rollouts of a Step in their own one-thread-per-
+  // instance kernels (Launch): within one wave the step is the latency of ONE solve and two extra launches only add to
+  // it.  The closed loop gains less (its fused form has no tail per control tick: warps run on into the next tick) and
+  // breaks even at about two waves (profiles/r02_x_ab_split_thresholds.jsonl).  Results do not depend on the choice.
+  h->split = batch > n_groups;
+  h->split_loop = batch >= 2 * n_groups;
   if ((flags & CPMPC_FLAG_SPLIT_LAUNCH) != 0u) h->split = h->split_loop = true;
   if ((flags & CPMPC_FLAG_FUSED_LAUNCH) != 0u) h->split = h->split_loop = false;
   if (const char* env = std::getenv("CPMPC_SPLIT")) h->split = h->split_loop = std::atoi(env) != 0;

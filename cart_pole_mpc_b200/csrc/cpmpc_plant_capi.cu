@@ -320,8 +320,8 @@ int cpmpc_plant_create(int plant, const cpmpc_plant_params* params, int64_t batc
   CPMPC_CUDA_TRY(cudaMemset(h->d_has_prev, 0, batch));
   CPMPC_CUDA_TRY(cudaMemset(h->d_prev, 0, sizeof(double) * batch * k.N));
   CPMPC_CUDA_TRY(cudaMalloc(&h->d_kk, sizeof(double) * n_groups * k.kk_stride));
-  // split launch from two waves of the persistent grid, as in cpmpc_create_ex; results do not depend on it
-  h->split = batch >= 2 * n_groups;
+  // split launch beyond one wave of the persistent grid, as in cpmpc_create_ex; results do not depend on it
+  h->split = batch > n_groups;
   if (const char* env = std::getenv("CPMPC_SPLIT")) h->split = std::atoi(env) != 0;
   if (h->split) {
     CPMPC_CUDA_TRY(cudaMalloc(&h->d_guess, sizeof(double) * batch * h->nx * k.NS));

@@ -103,7 +103,12 @@ def loop_workload(B, ticks, split, reps=3):
 
 
 WORKLOADS = {
+    "config2_8192": lambda sp: step_workload(8192, sp),
+    "config2_10240": lambda sp: step_workload(10240, sp),
+    "config2_12288": lambda sp: step_workload(12288, sp),
     "config2_16384": lambda sp: step_workload(16384, sp),
+    "config2_24576": lambda sp: step_workload(24576, sp),
+    "closed_loop_32768x10": lambda sp: loop_workload(32768, 10, sp),
     "config2_65536": lambda sp: step_workload(65536, sp),
     "config2_262144": lambda sp: step_workload(262144, sp, reps=3),
     "config2_warm_65536": lambda sp: step_workload(65536, sp, warm=True),
