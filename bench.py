@@ -62,7 +62,7 @@ def algorithmic_flops(n_iter, n_ls, W=40, S=10, n_te=3, n_cost=81, nx=4, C_f=76,
     return n_iter * (F_lin + F_qp + F_dir) + n_ls * F_merit + 2 * F_roll
 
 
-NCU_SUMMARY = "profiles/r02_final.json"
+NCU_SUMMARY = "profiles/r02_w_final.json"
 
 
 def headline_config(B, allgather=False):
@@ -97,14 +97,14 @@ def ncu_dram_traffic(batch):
 
 def ncu_fp64_ops(workload, batch):
     """Executed DFMA / DMUL / DADD thread instructions of one launch from the committed ncu capture of this build
-    (profiles/r02_fp64_ops.json: {"config2": {"batch":..., "dfma":..., "dmul":..., "dadd":...}, ...}), scaled to flops
+    (profiles/r02_y_fp64_ops.json: {"config2": {"batch":..., "dfma":..., "dmul":..., "dadd":...}, ...}), scaled to flops
     per solve; None when the capture is missing."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r02_fp64_ops.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r02_y_fp64_ops.json")) as fh:
             rec = json.load(fh)[workload]
         fl = 2.0 * rec["dfma"] + rec["dmul"] + rec["dadd"]
         return {"flops_per_solve": fl / rec["batch"], "captured_at_batch": rec["batch"],
-                "source": "profiles/r02_fp64_ops.json (ncu smsp__sass_thread_inst_executed_op_d{fma,mul,add}_pred_on)"}
+                "source": "profiles/r02_y_fp64_ops.json (ncu smsp__sass_thread_inst_executed_op_d{fma,mul,add}_pred_on, all kernels of one step)"}
     except (OSError, KeyError, ValueError):
         return None
 
