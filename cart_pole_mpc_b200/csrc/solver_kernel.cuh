@@ -669,27 +669,61 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, boo
     }
   }
   tri_valid = true;
-  // (2) rows of U: sensitivity of the terminal node to every control, through the later segments
-  #pragma unroll 1
-  for (int col = c.gl; col < W; col += L) {
-    const int s = col / S;
-    double v0 = Gam[col], v1 = Gam[W + col], v2 = Gam[2 * W + col], v3 = Gam[3 * W + col];
+  // (2) rows of U: sensitivity of the terminal node to every control, through the later segments.  Two columns of
+  // this lane per trip (col and col + L: the same or neighbouring segments), so that the products of one column fill
+  // the FMA latency of the other; the segment index is carried along instead of divided out.  Per column the same
+  // operations in the same order as one column at a time.
+  {
+    int col = c.gl, sa = 0, sa_end = S;  // sa = col / S
     #pragma unroll 1
-    for (int t = s + 1; t < nseg; ++t) {
-      const double* Ph = Phi + 16 * t;
-      const double n0 = Ph[0] * v0 + Ph[1] * v1 + Ph[2] * v2 + Ph[3] * v3;
-      const double n1 = Ph[4] * v0 + Ph[5] * v1 + Ph[6] * v2 + Ph[7] * v3;
-      const double n2 = Ph[8] * v0 + Ph[9] * v1 + Ph[10] * v2 + Ph[11] * v3;
-      const double n3 = Ph[12] * v0 + Ph[13] * v1 + Ph[14] * v2 + Ph[15] * v3;
-      v0 = n0;
-      v1 = n1;
-      v2 = n2;
-      v3 = n3;
+    for (; col < W; col += 2 * L) {
+      while (col >= sa_end) {
+        ++sa;
+        sa_end += S;
+      }
+      const int colb = col + L;
+      const bool hb = colb < W;
+      const int cb = hb ? colb : col;
+      int sb = sa;
+      if (cb >= sa_end) ++sb;  // L <= S in every mapping: at most one boundary between the two columns
+      if (cb >= sa_end + S) sb = cb / S;  // (not reached while L <= S; kept for safety)
+      double v0 = Gam[col], v1 = Gam[W + col], v2 = Gam[2 * W + col], v3 = Gam[3 * W + col];
+      double y0 = Gam[cb], y1 = Gam[W + cb], y2 = Gam[2 * W + cb], y3 = Gam[3 * W + cb];
+      #pragma unroll 1
+      for (int t = sa + 1; t < nseg; ++t) {
+        const double* Ph = Phi + 16 * t;
+        const double p0 = Ph[0], p1 = Ph[1], p2 = Ph[2], p3 = Ph[3], p4 = Ph[4], p5 = Ph[5], p6 = Ph[6], p7 = Ph[7];
+        const double p8 = Ph[8], p9 = Ph[9], p10 = Ph[10], p11 = Ph[11], p12 = Ph[12], p13 = Ph[13], p14 = Ph[14],
+                     p15 = Ph[15];
+        const double n0 = p0 * v0 + p1 * v1 + p2 * v2 + p3 * v3;
+        const double n1 = p4 * v0 + p5 * v1 + p6 * v2 + p7 * v3;
+        const double n2 = p8 * v0 + p9 * v1 + p10 * v2 + p11 * v3;
+        const double n3 = p12 * v0 + p13 * v1 + p14 * v2 + p15 * v3;
+        const double m0 = p0 * y0 + p1 * y1 + p2 * y2 + p3 * y3;
+        const double m1 = p4 * y0 + p5 * y1 + p6 * y2 + p7 * y3;
+        const double m2 = p8 * y0 + p9 * y1 + p10 * y2 + p11 * y3;
+        const double m3 = p12 * y0 + p13 * y1 + p14 * y2 + p15 * y3;
+        v0 = n0;
+        v1 = n1;
+        v2 = n2;
+        v3 = n3;
+        const bool ub = t > sb;
+        y0 = ub ? m0 : y0;
+        y1 = ub ? m1 : y1;
+        y2 = ub ? m2 : y2;
+        y3 = ub ? m3 : y3;
+      }
+      Z[col] = v0;
+      Z[W + col] = v1;
+      Z[2 * W + col] = v2;
+      Z[3 * W + col] = v3;
+      if (hb) {
+        Z[colb] = y0;
+        Z[W + colb] = y1;
+        Z[2 * W + colb] = y2;
+        Z[3 * W + colb] = y3;
+      }
     }
-    Z[col] = v0;
-    Z[W + col] = v1;
-    Z[2 * W + col] = v2;
-    Z[3 * W + col] = v3;
   }
   // node steps for du = 0: m_0 = -(x_0 - x_cur), m_{s+1} = Phi_s m_s + e_s (every lane, registers)
   double m[4];
@@ -848,12 +882,28 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, boo
 
   // (6) du = -L^-T D^-1 (z_g + Z sigma); c_u . du = -(L^-1 g)^T D^-1 (z_g + Z sigma) needs no second pass over g
   double part = 0.0;
-  #pragma unroll 1
-  for (int q = c.gl; q < W; q += L) {
-    const double zg = du[q];
-    const double wq = (zg + sig[0] * Z[q] + sig[1] * Z[W + q] + sig[2] * Z[2 * W + q] + sig[3] * Z[3 * W + q]) * tinv[q];
-    part = fma(zg, wq, part);
-    du[q] = wq;
+  {
+    // two columns per trip with all loads ahead of the stores; the sum `part` runs over the columns in the same order
+    int q = c.gl;
+    #pragma unroll 1
+    for (; q + L < W; q += 2 * L) {
+      const int qb = q + L;
+      const double zga = du[q], zgb = du[qb], tia = tinv[q], tib = tinv[qb];
+      const double a0 = Z[q], a1 = Z[W + q], a2 = Z[2 * W + q], a3 = Z[3 * W + q];
+      const double b0 = Z[qb], b1 = Z[W + qb], b2 = Z[2 * W + qb], b3 = Z[3 * W + qb];
+      const double wa = (zga + sig[0] * a0 + sig[1] * a1 + sig[2] * a2 + sig[3] * a3) * tia;
+      const double wb = (zgb + sig[0] * b0 + sig[1] * b1 + sig[2] * b2 + sig[3] * b3) * tib;
+      part = fma(zga, wa, part);
+      part = fma(zgb, wb, part);
+      du[q] = wa;
+      du[qb] = wb;
+    }
+    if (q < W) {
+      const double zg = du[q];
+      const double wq = (zg + sig[0] * Z[q] + sig[1] * Z[W + q] + sig[2] * Z[2 * W + q] + sig[3] * Z[3 * W + q]) * tinv[q];
+      part = fma(zg, wq, part);
+      du[q] = wq;
+    }
   }
   cdx = -part;  // this lane's share of c_u . du
   CPMPC_GSYNC();
@@ -1355,8 +1405,17 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
           xc[4 * q + 2] = __dadd_rn(xs[4 * q + 2], __dmul_rn(dxs[4 * q + 2], alpha));
           xc[4 * q + 3] = __dadd_rn(xs[4 * q + 3], __dmul_rn(dxs[4 * q + 3], alpha));
         }
-        for (int col = c.gl; col < W; col += L)
-          uc[col] = clampd(__dadd_rn(u[col], __dmul_rn(du[col], alpha)), -k.u_clamp, k.u_clamp);
+        {
+          // two columns per trip, loads ahead of the stores (uc aliases neither u nor du, but the compiler cannot know)
+          int col = c.gl;
+          #pragma unroll 1
+          for (; col + L < W; col += 2 * L) {
+            const double ua = u[col], ub = u[col + L], da = du[col], db = du[col + L];
+            uc[col] = clampd(__dadd_rn(ua, __dmul_rn(da, alpha)), -k.u_clamp, k.u_clamp);
+            uc[col + L] = clampd(__dadd_rn(ub, __dmul_rn(db, alpha)), -k.u_clamp, k.u_clamp);
+          }
+          if (col < W) uc[col] = clampd(__dadd_rn(u[col], __dmul_rn(du[col], alpha)), -k.u_clamp, k.u_clamp);
+        }
         CPMPC_GSYNC();
         CPMPC_PARK();
         evaluate_errors<L>(c, w, xc, uc, xkc, x_cur, set_point, u_prev, step_f, step_eq);
