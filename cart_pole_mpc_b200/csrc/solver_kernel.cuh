@@ -787,10 +787,8 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, boo
   {
     // pair list: (0,0)(0,1)(0,2)(0,3)(1,1)(1,2)(1,3)(2,2)(2,3)(3,3)(0,4)(1,4)(2,4)(3,4)
     // every lane accumulates over its own columns q = gl, gl + L, ...; a group sum finishes each entry
-    #pragma unroll 1
-    for (int q = c.gl; q < W; q += L) {
-      const double ti = tinv[q];
-      const double z0 = Z[q], z1 = Z[W + q], z2 = Z[2 * W + q], z3 = Z[3 * W + q], zg = du[q];
+    auto gram_col = [&](const double z0, const double z1, const double z2, const double z3, const double zg,
+                        const double ti) {
       const double s0 = z0 * ti, s1 = z1 * ti, s2 = z2 * ti, s3 = z3 * ti;
       gm[0] = fma(s0, z0, gm[0]);
       gm[1] = fma(s0, z1, gm[1]);
@@ -806,7 +804,18 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, boo
       gm[11] = fma(s1, zg, gm[11]);
       gm[12] = fma(s2, zg, gm[12]);
       gm[13] = fma(s3, zg, gm[13]);
+    };
+    int q = c.gl;
+    #pragma unroll 1
+    for (; q + L < W; q += 2 * L) {  // two columns per trip: the loads of the second ahead of the sums of the first
+      const int qb = q + L;
+      const double tia = tinv[q], tib = tinv[qb], zga = du[q], zgb = du[qb];
+      const double a0 = Z[q], a1 = Z[W + q], a2 = Z[2 * W + q], a3 = Z[3 * W + q];
+      const double b0 = Z[qb], b1 = Z[W + qb], b2 = Z[2 * W + qb], b3 = Z[3 * W + qb];
+      gram_col(a0, a1, a2, a3, zga, tia);
+      gram_col(b0, b1, b2, b3, zgb, tib);
     }
+    if (q < W) gram_col(Z[q], Z[W + q], Z[2 * W + q], Z[3 * W + q], du[q], tinv[q]);
 #pragma unroll
     for (int e = 0; e < 14; ++e) gm[e] = group_sum<L>(gm[e], c.gmask);
   }
@@ -949,6 +958,15 @@ __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, boo
       const double* vv = du + s * S;
       int j = 0;
       #pragma unroll 1
+      for (; j + 3 < S; j += 4) {  // four products per trip, their eight loads first; the two sums keep their order
+        const double g0 = ga[j], g1 = ga[j + 1], g2 = ga[j + 2], g3 = ga[j + 3];
+        const double w0 = vv[j], w1 = vv[j + 1], w2 = vv[j + 2], w3 = vv[j + 3];
+        n0 = fma(g0, w0, n0);
+        n1 = fma(g1, w1, n1);
+        n0 = fma(g2, w2, n0);
+        n1 = fma(g3, w3, n1);
+      }
+      #pragma unroll 1
       for (; j + 1 < S; j += 2) {
         n0 = fma(ga[j], vv[j], n0);
         n1 = fma(ga[j + 1], vv[j + 1], n1);
@@ -1046,8 +1064,16 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
     // branch-free (weights of absent cost families are 0): the rate residual behind the last knot is formed against the
     // knot itself, the one in front of knot 0 against the previous step's control
     const double wr2 = w.w_r * w.w_r, wu2 = w.w_u * w.w_u;
+    int col = c.gl;
     #pragma unroll 1
-    for (int col = c.gl; col < W; col += L) {
+    for (; col + L < W; col += 2 * L) {  // two columns per trip, loads ahead of the stores
+      const int cb = col + L;
+      const double uk = u[col], un = u[col + 1], up = (col > 0) ? u[col - 1] : u_prev;
+      const double vk = u[cb], vn = u[(cb + 1 < W) ? cb + 1 : cb], vp = u[cb - 1];
+      du[col] = wr2 * (uk - un) + wr2 * (uk - up) + wu2 * uk;
+      du[cb] = wr2 * (vk - vn) + wr2 * (vk - vp) + wu2 * vk;
+    }
+    if (col < W) {
       const double uk = u[col];
       const double un = u[(col + 1 < W) ? col + 1 : col];
       const double up = (col > 0) ? u[col - 1] : u_prev;
