@@ -1838,7 +1838,7 @@ __device__ __forceinline__ DynConst make_dyn_const_opaque(const double* __restri
 // controls (warm start shifted by one knot, optimization.cc:57-61, or the cold-start guess), same rk4_step, same order:
 // the shooting states are bit-identical to the fused path's (profiles/ab_compare.py).
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) cpmpc_guess_kernel(const KernelCfg cfg, const KernelIO io, double* __restrict__ guess) {
+__global__ void __launch_bounds__(128, 4) cpmpc_guess_kernel(const KernelCfg cfg, const KernelIO io, double* __restrict__ guess) {
   const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (inst >= io.B) return;
   const int W = cfg.W, S = cfg.S, NS = cfg.NS, N = cfg.N;
@@ -1869,7 +1869,7 @@ __global__ void __launch_bounds__(128) cpmpc_guess_kernel(const KernelCfg cfg, c
 // Simulator::Step(control_dt, u[0]) with 1 ms sub-steps (simulator.cc:11-36), one THREAD per instance, from the controls
 // the solve kernel left in u[B, W].
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) cpmpc_post_kernel(const KernelCfg cfg, const KernelIO io, const double* __restrict__ u) {
+__global__ void __launch_bounds__(128, 4) cpmpc_post_kernel(const KernelCfg cfg, const KernelIO io, const double* __restrict__ u) {
   const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (inst >= io.B) return;
   const int W = cfg.W;

@@ -15,6 +15,9 @@ import torch  # noqa: E402
 
 from cart_pole_mpc_b200 import BatchedOptimization, _capi, synthetic  # noqa: E402
 
+if os.environ.get("SWEEP_LIB"):  # A/B of two builds of the library on the same box (a tool switch, not the product's)
+    _capi.LIB_PATH = os.path.abspath(os.environ["SWEEP_LIB"])
+
 
 def run(B, reps=20, first=0, **kw):
     states, dyn, sp = synthetic.swingup_batch(B, first=first)

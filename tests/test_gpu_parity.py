@@ -879,3 +879,30 @@ def test_compact_shared_memory_layout_equals_roomy_layout(over, monkeypatch):
             assert outs[0][k].stats.tobytes() == other[k].stats.tobytes(), k
     if over.get("u_cost_weight") == 0.0:
         assert (outs[0][0].stats["lambda"] > 0).any() or (outs[0][0].stats["n_failed_line_searches"] > 0).any()
+
+
+def test_pipelined_steps_with_split_launch_equal_fused_synchronous_steps():
+    """cpmpc_step_async / cpmpc_wait on a handle that uses the split launch (the three kernels of a step and the shared
+    guess buffer are chained behind the previous step's kernels): the same bits as synchronous fused steps."""
+    import torch
+    from cart_pole_mpc_b200 import BatchedOptimization, synthetic, _capi
+    B, W, T = 300, 40, 4
+    st, dy, sp = synthetic.swingup_batch(B, seed=21)
+    states = [st + 0.01 * t for t in range(T)]
+    ref = BatchedOptimization(B, split_launch=False)
+    want = [ref.step(states[t], dy, sp) for t in range(T)]
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    s = BatchedOptimization(B, split_launch=True)
+    ins = [pin(x) for x in states]
+    dyp, spp = pin(dy), pin(sp)
+    u = [pin(np.zeros((B, W))) for _ in range(T)]
+    pred = [pin(np.zeros((B, W, 4))) for _ in range(T)]
+    stats = [pin(np.zeros(B, dtype=_capi.STATS_DTYPE).view(np.uint8)) for _ in range(T)]
+    for t in range(T):
+        s.step_async(ins[t], dyp, spp, u[t], pred_out=pred[t], stats_out=stats[t])
+    s.wait()
+    s.wait()
+    for t in range(T):
+        assert np.array_equal(u[t], want[t].u, equal_nan=True), t
+        assert np.array_equal(pred[t], want[t].predicted_states, equal_nan=True), t
+        assert stats[t].tobytes() == want[t].stats.tobytes(), t
