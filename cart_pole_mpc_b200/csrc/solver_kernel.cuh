@@ -546,7 +546,10 @@ __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights& w, const
   // rows of a segment: S * GAIN_STRIDE doubles, staged k.stage_knots knots at a time (a whole segment unless shared
   // memory is short); when a whole segment fits NPF per lane it is prefetched into registers one segment ahead, so the L2
   // round trip of segment s + 1 overlaps the first lane's work on segment s
-  constexpr int NPF = 4;
+  // (S = 10 knots are 100 doubles: 13 per lane of an 8-lane group, the W = 160 mapping, where the recursion runs on
+  // every iteration: 8 % of that step.  Not for 4-lane groups: 25 more live doubles per lane cost the default problem,
+  // which takes the recursion on damped iterations only, 9 % of its step through the register allocation.)
+  constexpr int NPF = (L == 16) ? 7 : (L == 8) ? 13 : 4;
   const int n_rows = S * GAIN_STRIDE;
   const int SK = k.stage_knots;
   const bool fits = n_rows <= NPF * L && SK == S;
