@@ -906,3 +906,38 @@ def test_pipelined_steps_with_split_launch_equal_fused_synchronous_steps():
         assert np.array_equal(u[t], want[t].u, equal_nan=True), t
         assert np.array_equal(pred[t], want[t].predicted_states, equal_nan=True), t
         assert stats[t].tobytes() == want[t].stats.tobytes(), t
+
+
+def test_large_batch_launch_shape_properties_and_parity(oracle):
+    """65536 cold swing-ups (BASELINE.json's supplementary size): the library picks the split launch and the compact
+    shared-memory layout by itself.  Size-independent properties, determinism, batch-composition independence against
+    the single-wave mapping (instance i of the big batch == instance i solved in a batch of a few hundred, bit for bit),
+    and parity of a sample with the compiled reference at the headline tolerance."""
+    from cart_pole_mpc_b200 import launch_count, synthetic
+    B = 65536
+    st, dy, sp = synthetic.swingup_batch(B)
+    s = _solver(B)
+    n0 = launch_count()
+    out = s.step(st, dy, sp)
+    assert launch_count() - n0 == 3, "guess, solve and predicted-state kernels"
+    assert np.all(np.isfinite(out.u)) and np.all(np.abs(out.u) <= 300.0)
+    ls, it = out.stats["n_line_search_steps"], out.stats["n_iterations"]
+    assert np.all((it >= 1) & (it <= 8)) and np.all(ls >= it) and np.all(ls <= 6 * it)
+    th = out.predicted_states[:, :, 1]
+    fin = np.isfinite(th)
+    assert fin.mean() > 0.999 and np.all((th[fin] > -math.pi - 1e-12) & (th[fin] <= math.pi + 1e-12))
+    sol, has = s.get_previous_solution()
+    assert has.all() and np.array_equal(sol[:, -40:], out.u)
+    s.reset()
+    out2 = s.step(st, dy, sp)
+    assert np.array_equal(out.u, out2.u) and out.stats.tobytes() == out2.stats.tobytes()
+    s.close()
+    idx = np.r_[0:64, 4090:4100, 30000:30128, 65472:65536]
+    small = _solver(len(idx)).step(st[idx], dy[idx], sp[idx])
+    assert np.array_equal(small.u, out.u[idx])
+    assert np.array_equal(small.predicted_states, out.predicted_states[idx], equal_nan=True)
+    assert small.stats.tobytes() == out.stats[idx].tobytes()
+    if oracle.ref_available():
+        with oracle.using_ref():
+            ref = oracle.batch_step(oracle.opt_array(), st[idx], dy[idx], sp[idx], want_iter_log=False)
+        _check_batch(small, ref.stats, ref.u, min_frac=0.93)
