@@ -254,6 +254,23 @@ CPMPC_DEV void dyn_eval_jac(const DynConst& P, const double b_x, const double th
   fth[3] = (dq_x_dw * s_over_l + tth_w * P.kappa) * inv_d;
 }
 
+// The branch-free sincos of fastmath.cuh is valid for |x| < 2^20.  Angles the integrator produces stay far inside (every
+// step ends in mod_pi), but a caller may hand in any finite pole angle: states are passed through this on the way into
+// a kernel.  sin / cos and the wrapped angle differences of the problem do not see the wrap (the reference evaluates
+// libm sin / cos on the raw angle: the same value up to the rounding of 2 pi in the reduction, 1e-10 rad at 2^21).  For
+// angles inside the range - every one a controller will ever see - nothing changes, not even the bits.
+// The wrap itself is an out-of-line call behind a branch that is never taken in practice: inlined into the prologue of
+// the solve kernel its software fmod moves that kernel's register allocation (1 % of the step, measured).
+#if defined(__CUDACC__)
+static __device__ __noinline__ double wrap_far_angle_slow(double th) { return mod_pi(th); }
+__device__ __forceinline__ double wrap_far_angle(double th) {
+  if (!(fabs(th) < 1048576.0)) th = wrap_far_angle_slow(th);
+  return th;
+}
+#else
+inline double wrap_far_angle(double th) { return (fabs(th) < 1048576.0) ? th : mod_pi(th); }
+#endif
+
 // One classic RK4 step, in place, no Jacobians (integration.hpp:53-62).  The four stages run as a rolled loop around
 // ONE inlined copy of the dynamics so the hot code stays inside the instruction cache.
 template <bool FORCES>

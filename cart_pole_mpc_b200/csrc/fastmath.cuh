@@ -200,6 +200,9 @@ CPMPC_HD void sincos_bf(double x, double& s_out, double& c_out) {
 }
 
 // tanh(x) with ABSOLUTE error ~2e-16 (enough here: it multiplies the friction force inside a sum of O(1) forces).
+// A NaN argument gives +-1, not NaN (fmin drops it).  The only caller passes the cart velocity, which the same RK4 stage
+// also adds to the cart position, so a NaN still reaches the state, the cost and the non-finite rejection
+// (nonlinear.cc:356-357) without an extra select in the hottest function of the kernel.
 CPMPC_HD double tanh_bf(double x) {
   const double ax = fmin(fabs(x), 20.0);
   const double y = -2.0 * ax;  // em = exp(y) in (4e-18, 1]

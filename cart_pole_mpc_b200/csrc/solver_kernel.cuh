@@ -1623,6 +1623,7 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
       const double* ps = (io.sim ? io.states_io : io.states) + inst * CPMPC_STATE_STRIDE;
 #pragma unroll
       for (int i = 0; i < 4; ++i) x_cur[i] = ps[i];
+      x_cur[1] = wrap_far_angle(x_cur[1]);
       set_point = io.set_points[inst];
     } else {
       if (c.gl == 0) store_dyn_const(c.sm + cfg.off_dyn, dummy_dyn_const());
@@ -1847,7 +1848,7 @@ __global__ void __launch_bounds__(128, 4) cpmpc_guess_kernel(const KernelCfg cfg
   const int W = cfg.W, S = cfg.S, NS = cfg.NS, N = cfg.N;
   const DynConst P = make_dyn_const_opaque(io.dyn + inst * CPMPC_DYN_STRIDE);
   const double* ps = (io.sim ? io.states_io : io.states) + inst * CPMPC_STATE_STRIDE;
-  double x[4] = {ps[0], ps[1], ps[2], ps[3]};
+  double x[4] = {ps[0], wrap_far_angle(ps[1]), ps[2], ps[3]};
   const bool warm = io.has_prev[inst] != 0;
   const double* pu = warm ? io.prev + inst * N + 4 * NS : io.u_guess;
   double* gx = guess + inst * (4 * NS);
@@ -1878,7 +1879,7 @@ __global__ void __launch_bounds__(128, 4) cpmpc_post_kernel(const KernelCfg cfg,
   const int W = cfg.W;
   const DynConst P = make_dyn_const_opaque(io.dyn + inst * CPMPC_DYN_STRIDE);
   const double* ps = (io.sim ? io.states_io : io.states) + inst * CPMPC_STATE_STRIDE;
-  const double x0[4] = {ps[0], ps[1], ps[2], ps[3]};
+  const double x0[4] = {ps[0], wrap_far_angle(ps[1]), ps[2], ps[3]};
   const double* pu = u + inst * W;
   if (io.pred_out != nullptr) {
     double x[4] = {x0[0], x0[1], x0[2], x0[3]};
@@ -1920,7 +1921,7 @@ __global__ void cpmpc_sim_kernel(const long long B, double* __restrict__ states,
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
   const DynConst P = make_dyn_const(dyn + i * CPMPC_DYN_STRIDE);
-  double x[4] = {states[4 * i], states[4 * i + 1], states[4 * i + 2], states[4 * i + 3]};
+  double x[4] = {states[4 * i], wrap_far_angle(states[4 * i + 1]), states[4 * i + 2], states[4 * i + 3]};
   const double ui = u[i];
   const double fbx = f_base ? f_base[2 * i] : 0.0;
   const double fmx = f_mass ? f_mass[2 * i] : 0.0;

@@ -941,3 +941,29 @@ def test_large_batch_launch_shape_properties_and_parity(oracle):
         with oracle.using_ref():
             ref = oracle.batch_step(oracle.opt_array(), st[idx], dy[idx], sp[idx], want_iter_log=False)
         _check_batch(small, ref.stats, ref.u, min_frac=0.93)
+
+
+def test_far_out_pole_angles_are_wrapped_on_the_way_in(oracle):
+    """A caller may pass any finite pole angle; the kernel's branch-free sincos is valid for |x| < 2^20 only, so states
+    are wrapped on the way into every kernel (csrc/dynamics.cuh wrap_far_angle).  The solve from th = 2^21 + x equals
+    the solve from the wrapped angle bit for bit, and agrees with the reference (libm sin / cos on the raw angle) to
+    the rounding of 2 pi in the reduction."""
+    from cart_pole_mpc_b200 import synthetic, sim_step
+    B = 64
+    st, dy, sp = synthetic.swingup_batch(B, seed=5)
+    far = st.copy()
+    far[:, 1] = 2.0 ** 21 + np.linspace(-3.0, 3.0, B)
+    two_pi, pi = 6.283185307179586, 3.141592653589793
+    w = np.fmod(far[:, 1], two_pi)
+    w = np.where(w < 0.0, w + two_pi, w)
+    w = np.where(w > pi, w - two_pi, w)
+    wrapped = far.copy()
+    wrapped[:, 1] = w
+    a = _solver(B).step(far, dy, sp)
+    b = _solver(B).step(wrapped, dy, sp)
+    assert np.array_equal(a.u, b.u) and np.array_equal(a.predicted_states, b.predicted_states)
+    assert a.stats.tobytes() == b.stats.tobytes()
+    assert np.array_equal(sim_step(far, dy, a.u[:, 0], 0.01), sim_step(wrapped, dy, a.u[:, 0], 0.01))
+    ref = oracle.batch_step(oracle.opt_array(), far, dy, sp, want_iter_log=False)
+    rel = _rel_cost(a, ref.stats)
+    assert np.median(rel) < 1e-6 and (rel <= 1e-4).mean() >= 0.9, rel
