@@ -62,7 +62,7 @@ def algorithmic_flops(n_iter, n_ls, W=40, S=10, n_te=3, n_cost=81, nx=4, C_f=76,
     return n_iter * (F_lin + F_qp + F_dir) + n_ls * F_merit + 2 * F_roll
 
 
-NCU_SUMMARY = "profiles/r02_w_final.json"
+NCU_SUMMARY = "profiles/r02_y_final.json"
 
 
 def headline_config(B, allgather=False):
