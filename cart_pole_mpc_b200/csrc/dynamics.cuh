@@ -124,11 +124,17 @@ CPMPC_DEV DynConst dummy_dyn_const() {
 }
 
 // Map an angle to (-pi, pi].  fmod(a, 2pi) == a exactly whenever |a| < 2pi, which skips CUDA's software fmod on
-// the overwhelmingly common path.
+// the overwhelmingly common path.  On the device the fmod is an out-of-line call: inlined, its expansion was 1249 of
+// the solve kernel's 11640 instructions (a copy of about 70 in every rollout loop, jumped over every time).
+#if defined(__CUDACC__)
+static __device__ __noinline__ double fmod_two_pi(double a) { return fmod(a, 6.283185307179586); }
+#else
+inline double fmod_two_pi(double a) { return fmod(a, 6.283185307179586); }
+#endif
 CPMPC_DEV double mod_pi(double a) {
   constexpr double pi = 3.141592653589793;
   constexpr double two_pi = 6.283185307179586;
-  if (!(fabs(a) < two_pi)) a = fmod(a, two_pi);
+  if (!(fabs(a) < two_pi)) a = fmod_two_pi(a);
   a += (a < 0.0) ? two_pi : 0.0;
   a -= (a > pi) ? two_pi : 0.0;
   return a;

@@ -27,6 +27,21 @@
 namespace cpmpc {
 namespace gp {
 
+// mod_pi with the fmod expanded in place, as this file has always been compiled (cpmpc::mod_pi calls it out of line
+// since round 2, which is worth 2 % to the single-pendulum kernel at large batches).  The value is the same function
+// (profiles/microbench/fmod_probe.cu: 2^20 arguments, inline == call == host libm), but this translation unit's
+// dynamics are plain `a * b + c` expressions whose multiply-add contraction is the compiler's choice, and that choice
+// moved with the surrounding code: the double pendulum's results changed in the last bits (then grew, as they do on a
+// chaotic plant).  Keeping the old form keeps this kernel's bits from build to build.
+CPMPC_DEV double mod_pi(double a) {
+  constexpr double pi = 3.141592653589793;
+  constexpr double two_pi = 6.283185307179586;
+  if (!(fabs(a) < two_pi)) a = fmod(a, two_pi);
+  a += (a < 0.0) ? two_pi : 0.0;
+  a -= (a > pi) ? two_pi : 0.0;
+  return a;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Plants
 // ---------------------------------------------------------------------------------------------------------------------
