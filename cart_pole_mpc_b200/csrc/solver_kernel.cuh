@@ -214,7 +214,9 @@ __device__ __forceinline__ void boundary_terms(const KernelCfg& k, const Weights
 // double temporaries, i.e. its four dependent chains strictly one after the other.  Behind a call boundary the body
 // gets the whole register file (the caller's live values are saved around the call: a few hundred cycles per
 // 10-step rollout).  Returns this lane's share of the L1 norm of the shooting defects.
-template <int L>
+// CHUNKED: the mapping splits segments into chunks (cps > 1, the latency mappings) and the chunk-start states are
+// recorded on the way; the throughput mapping's copy of the loop carries none of that.
+template <int L, bool CHUNKED>
 __device__ __forceinline__ double rollout_defects(const double* __restrict__ dynp, const double* __restrict__ xx,
                                                const double* __restrict__ uu, double* __restrict__ xk_out,
                                                const int gl, const int nseg, const int S, const int cps,
@@ -225,9 +227,9 @@ __device__ __forceinline__ double rollout_defects(const double* __restrict__ dyn
   for (int s = gl; s < nseg; s += L) {
     double x[4] = {xx[4 * s], xx[4 * s + 1], xx[4 * s + 2], xx[4 * s + 3]};
     int cc = 1;
-    int nb = (cps > 1) ? (S / cps) : S;  // first step of chunk cc
+    int nb = CHUNKED ? (S / cps) : S;  // first step of chunk cc
     for (int i = 0; i < S; ++i) {
-      if (i == nb) {
+      if (CHUNKED && i == nb) {
         double* dst = xk_out + 4 * (s * cps + cc);
         dst[0] = x[0];
         dst[1] = x[1];
@@ -254,7 +256,8 @@ __device__ __forceinline__ void evaluate_errors(const Ctx& c, const Weights& w, 
                                                 const double set_point, const double u_prev, double& f_out,
                                                 double& eq_out) {
   const KernelCfg& k = *c.cfg;
-  double eq = rollout_defects<L>(c.sm + k.off_dyn, xx, uu, xk_out, c.gl, k.nseg, k.S, k.cps, k.dt);
+  double eq = (k.cps > 1) ? rollout_defects<L, true>(c.sm + k.off_dyn, xx, uu, xk_out, c.gl, k.nseg, k.S, k.cps, k.dt)
+                          : rollout_defects<L, false>(c.sm + k.off_dyn, xx, uu, xk_out, c.gl, k.nseg, k.S, 1, k.dt);
   double f = control_cost_partial<L>(c, w, uu, u_prev);
   if (c.gl == 0) {
     double ft, eb;
