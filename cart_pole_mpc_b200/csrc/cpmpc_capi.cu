@@ -109,15 +109,21 @@ namespace {
 
 using KernelFn = void (*)(const KernelCfg, const KernelIO);
 
-KernelFn SelectKernel(int lanes) {
+// lean: the instantiation without the chunked linearisation, the iteration log, the debug view and the in-kernel plant
+// step (solver_kernel.cuh LEAN); Launch() picks it per launch whenever none of those is asked for.
+template <bool LEAN>
+KernelFn SelectKernelOf(int lanes) {
   switch (lanes) {
-    case 1: return cpmpc_solve_kernel<1>;
-    case 2: return cpmpc_solve_kernel<2>;
-    case 4: return cpmpc_solve_kernel<4>;
-    case 8: return cpmpc_solve_kernel<8>;
-    case 16: return cpmpc_solve_kernel<16>;
-    default: return cpmpc_solve_kernel<32>;
+    case 1: return cpmpc_solve_kernel<1, LEAN>;
+    case 2: return cpmpc_solve_kernel<2, LEAN>;
+    case 4: return cpmpc_solve_kernel<4, LEAN>;
+    case 8: return cpmpc_solve_kernel<8, LEAN>;
+    case 16: return cpmpc_solve_kernel<16, LEAN>;
+    default: return cpmpc_solve_kernel<32, LEAN>;
   }
+}
+KernelFn SelectKernel(int lanes, bool lean = false) {
+  return lean ? SelectKernelOf<true>(lanes) : SelectKernelOf<false>(lanes);
 }
 
 // Shared-memory layout of one instance (doubles).  `k.cps` must be set.
@@ -159,7 +165,6 @@ void BuildLayout(KernelCfg& k) {
 }
 
 int Launch(cpmpc_solver* h, KernelIO io, cudaStream_t stream) {
-  KernelFn fn = SelectKernel(h->lanes);
   io.B = h->B;
   io.u_guess = h->d_u_guess;
   io.prev = h->d_prev;
@@ -168,7 +173,10 @@ int Launch(cpmpc_solver* h, KernelIO io, cudaStream_t stream) {
   io.queue = h->d_queue;
   io.iter_log = h->log_enabled ? h->d_iter_log : nullptr;
   io.warp_cycles = h->d_warp_cycles;
-  if (!(io.sim ? h->split_loop : h->split) || io.dbg != nullptr) {
+  const bool split = (io.sim ? h->split_loop : h->split) && io.dbg == nullptr;
+  const bool lean = h->cfg.cps == 1 && io.iter_log == nullptr && io.dbg == nullptr && (io.sim == 0 || split);
+  KernelFn fn = SelectKernel(h->lanes, lean);
+  if (!split) {
     fn<<<h->grid, 32 * h->warps_per_block, h->smem_bytes, stream>>>(h->cfg, io);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
@@ -556,6 +564,8 @@ int cpmpc_create_ex(const cpmpc_params* params, int64_t batch, int device, uint3
   // instantiation but differ in warps per block must not lower each other's limit, so it is always set to the
   // device maximum.
   CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(prop.sharedMemPerBlockOptin)));
+  CUDA_TRY(cudaFuncSetAttribute(SelectKernel(lanes, true), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(prop.sharedMemPerBlockOptin)));
   int blocks_per_sm = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, 32 * wpb, h->smem_bytes));

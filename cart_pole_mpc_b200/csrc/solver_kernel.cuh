@@ -250,14 +250,15 @@ __device__ __forceinline__ double rollout_defects(const double* __restrict__ dyn
   return eq;
 }
 
-template <int L>
+template <int L, bool LEAN = false>
 __device__ __forceinline__ void evaluate_errors(const Ctx& c, const Weights& w, const double* xx,
                                                 const double* uu, double* xk_out, const double x_cur[4],
                                                 const double set_point, const double u_prev, double& f_out,
                                                 double& eq_out) {
   const KernelCfg& k = *c.cfg;
-  double eq = (k.cps > 1) ? rollout_defects<L, true>(c.sm + k.off_dyn, xx, uu, xk_out, c.gl, k.nseg, k.S, k.cps, k.dt)
-                          : rollout_defects<L, false>(c.sm + k.off_dyn, xx, uu, xk_out, c.gl, k.nseg, k.S, 1, k.dt);
+  double eq = (!LEAN && k.cps > 1)
+                  ? rollout_defects<L, true>(c.sm + k.off_dyn, xx, uu, xk_out, c.gl, k.nseg, k.S, k.cps, k.dt)
+                  : rollout_defects<L, false>(c.sm + k.off_dyn, xx, uu, xk_out, c.gl, k.nseg, k.S, 1, k.dt);
   double f = control_cost_partial<L>(c, w, uu, u_prev);
   if (c.gl == 0) {
     double ft, eb;
@@ -1004,7 +1005,10 @@ struct SolveResult {
 // On entry the shooting states, the chunk-start states and the control guess are in shared memory (xs, xk, u); on
 // exit xs/u hold the solution.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int L>
+// LEAN: the throughput mapping with nothing attached - one chunk per segment (cfg.cps == 1), no iteration log, no debug
+// view.  The host launches this instantiation whenever that holds (cpmpc_capi.cu SelectKernel); the paths it drops are
+// 40 % of the general kernel's instructions, never executed there but in the way of its register allocation.
+template <int L, bool LEAN = false>
 __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, const Weights& w,
                                             const double x_cur[4], const double& set_point, const double& u_prev,
                                             double* iter_log, SolveResult& res, long long* ph, double* dbg = nullptr,
@@ -1031,7 +1035,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
   double* Gam = c.sm + k.off_gam;
   constexpr double half_pi = 1.5707963267948966;
   const double target[4] = {set_point, half_pi, 0.0, 0.0};
-  const int W = k.W, S = k.S, NS = k.NS, nseg = k.nseg, cps = k.cps;
+  const int W = k.W, S = k.S, NS = k.NS, nseg = k.nseg, cps = LEAN ? 1 : k.cps;
 
   // Cold solver scalars: kept in a struct whose address escapes, so that CPMPC_PARK() moves them out of the
   // register file for the duration of the rollout loops (see CPMPC_PARK).
@@ -1450,7 +1454,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
         }
         CPMPC_GSYNC();
         CPMPC_PARK();
-        evaluate_errors<L>(c, w, xc, uc, xkc, x_cur, set_point, u_prev, step_f, step_eq);
+        evaluate_errors<L, LEAN>(c, w, xc, uc, xkc, x_cur, set_point, u_prev, step_f, step_eq);
         CPMPC_PARK();
         CPMPC_GSYNC();
         if (lrow != nullptr && c.gl == 0 && n_steps < 6) {
@@ -1550,8 +1554,11 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
 // ---------------------------------------------------------------------------------------------------------------------
 // Kernel: persistent grid-stride over instances; each warp carries 32/L instances at a time.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int L>
+template <int L, bool LEAN = false>
 __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg, const KernelIO io) {
+  // LEAN (see solve_group): additionally no plant step inside this kernel (no closed loop, or a split launch)
+  const bool sim_here = LEAN ? false : (io.sim != 0 && !io.split);
+  const int cps_guess = LEAN ? 1 : cfg.cps;
   const int WARPS_PER_BLOCK = blockDim.x >> 5;  // up to 8: two warps per SM sub-partition
   extern __shared__ double smem[];
   constexpr int G = 32 / L;
@@ -1672,15 +1679,15 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
           #pragma unroll 1
           for (int s = 1; s < NS; ++s) {
             int cc = 1;
-            int nb = (cfg.cps > 1) ? (S / cfg.cps) : S;
+            int nb = (cps_guess > 1) ? (S / cps_guess) : S;
             #pragma unroll 1
             for (int i = 0; i < S; ++i) {
               if (i == nb) {
-                double* dst = xk + 4 * ((s - 1) * cfg.cps + cc);
+                double* dst = xk + 4 * ((s - 1) * cps_guess + cc);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) dst[q] = x[q];
                 ++cc;
-                nb = (cc < cfg.cps) ? (cc * S) / cfg.cps : S;
+                nb = (cc < cps_guess) ? (cc * S) / cps_guess : S;
               }
               rk4_step<false>(Pl, x, u[(s - 1) * S + i], cfg.dt);
               x[1] = mod_pi(x[1]);
@@ -1693,23 +1700,23 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
       }
 
       SolveResult& res = kc.res;
-      double* ilog = (io.iter_log != nullptr && have)
+      double* ilog = (!LEAN && io.iter_log != nullptr && have)
                          ? io.iter_log + (size_t)inst * cfg.max_iter * CPMPC_ITERLOG_STRIDE
                          : nullptr;
-      double* dbg = (io.dbg != nullptr && have) ? io.dbg + (size_t)inst * io.dbg_stride : nullptr;
+      double* dbg = (!LEAN && io.dbg != nullptr && have) ? io.dbg + (size_t)inst * io.dbg_stride : nullptr;
       {
         const long long now = clock64();
         ph[0] += now - ph[N_PHASES];
         ph[N_PHASES] = now;
       }
-      solve_group<L>(c, have, w, x_cur, set_point, u_prev, ilog, res, ph, dbg, io.dbg_lambda, io.dbg_qp);
+      solve_group<L, LEAN>(c, have, w, x_cur, set_point, u_prev, ilog, res, ph, dbg, io.dbg_lambda, io.dbg_qp);
 
       if (have) {
         // ---- outputs (optimization.cc:83-96) ------------------------------------------------------------------
         // A rejected instance keeps its previous warm start: the reference throws inside Solve()
         // (nonlinear.cc:356-357) before previous_solution_ is assigned (optimization.cc:84-85).  The debug view
         // never touches the warm start either.
-        const bool keep = res.termination != TS_REJECTED && io.dbg == nullptr;
+        const bool keep = res.termination != TS_REJECTED && (LEAN || io.dbg == nullptr);
         double* prev = io.prev + inst * N;
         if (keep)
           #pragma unroll 1
@@ -1758,7 +1765,7 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
                       res.termination == TS_REJECTED)
                          ? 1
                          : 0;
-          if (io.sim && !io.split) {
+          if (sim_here) {
             // Simulator::Step(control_dt, u[0]) with 1 ms sub-steps (simulator.cc:11-36)
             const double u0 = u[0];
             if (io.controls_out != nullptr) io.controls_out[inst * io.n_steps + step] = u0;
@@ -1777,7 +1784,7 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
             for (int i = 0; i < 4; ++i) x_cur[i] = x[i];
           }
         }
-        if (io.sim && !io.split) {
+        if (sim_here) {
           const int src = (c.gmask == 0xffffffffu) ? 0 : (__ffs(c.gmask) - 1);
 #pragma unroll
           for (int i = 0; i < 4; ++i) x_cur[i] = __shfl_sync(c.gmask, x_cur[i], src);
@@ -1791,7 +1798,7 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
       }
     }
     if (have && c.gl == 0) {
-      if (io.sim && !io.split) {
+      if (sim_here) {
         double* ps = io.states_io + inst * CPMPC_STATE_STRIDE;
 #pragma unroll
         for (int i = 0; i < 4; ++i) ps[i] = x_cur[i];

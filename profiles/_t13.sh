@@ -7,3 +7,4 @@ SWEEP_LIB=cart_pole_mpc_b200/libcpmpc_base.so python profiles/lane_sweep.py 4096
 python profiles/lane_sweep.py 4096 65536
 done
 rm -f gpurun_out/ab_old.npz gpurun_out/ab_new.npz
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
