@@ -109,21 +109,23 @@ namespace {
 
 using KernelFn = void (*)(const KernelCfg, const KernelIO);
 
-// lean: the instantiation without the chunked linearisation, the iteration log, the debug view and the in-kernel plant
-// step (solver_kernel.cuh LEAN); Launch() picks it per launch whenever none of those is asked for.
-template <bool LEAN>
+// mode 0: the general kernel.  1: the lean instantiation - no chunked linearisation, iteration log, debug view or
+// in-kernel plant step (solver_kernel.cuh LEAN) - for every plain Step and the split closed loop.  2: lean with the
+// plant step, for the fused closed loop.  Launch() picks per launch.
+template <bool LEAN, bool SIM>
 KernelFn SelectKernelOf(int lanes) {
   switch (lanes) {
-    case 1: return cpmpc_solve_kernel<1, LEAN>;
-    case 2: return cpmpc_solve_kernel<2, LEAN>;
-    case 4: return cpmpc_solve_kernel<4, LEAN>;
-    case 8: return cpmpc_solve_kernel<8, LEAN>;
-    case 16: return cpmpc_solve_kernel<16, LEAN>;
-    default: return cpmpc_solve_kernel<32, LEAN>;
+    case 1: return cpmpc_solve_kernel<1, LEAN, SIM>;
+    case 2: return cpmpc_solve_kernel<2, LEAN, SIM>;
+    case 4: return cpmpc_solve_kernel<4, LEAN, SIM>;
+    case 8: return cpmpc_solve_kernel<8, LEAN, SIM>;
+    case 16: return cpmpc_solve_kernel<16, LEAN, SIM>;
+    default: return cpmpc_solve_kernel<32, LEAN, SIM>;
   }
 }
-KernelFn SelectKernel(int lanes, bool lean = false) {
-  return lean ? SelectKernelOf<true>(lanes) : SelectKernelOf<false>(lanes);
+KernelFn SelectKernel(int lanes, int mode = 0) {
+  return mode == 2 ? SelectKernelOf<true, true>(lanes)
+                   : mode == 1 ? SelectKernelOf<true, false>(lanes) : SelectKernelOf<false, true>(lanes);
 }
 
 // Shared-memory layout of one instance (doubles).  `k.cps` must be set.
@@ -174,8 +176,8 @@ int Launch(cpmpc_solver* h, KernelIO io, cudaStream_t stream) {
   io.iter_log = h->log_enabled ? h->d_iter_log : nullptr;
   io.warp_cycles = h->d_warp_cycles;
   const bool split = (io.sim ? h->split_loop : h->split) && io.dbg == nullptr;
-  const bool lean = h->cfg.cps == 1 && io.iter_log == nullptr && io.dbg == nullptr && (io.sim == 0 || split);
-  KernelFn fn = SelectKernel(h->lanes, lean);
+  const bool lean = h->cfg.cps == 1 && io.iter_log == nullptr && io.dbg == nullptr;
+  KernelFn fn = SelectKernel(h->lanes, lean ? ((io.sim != 0 && !split) ? 2 : 1) : 0);
   if (!split) {
     fn<<<h->grid, 32 * h->warps_per_block, h->smem_bytes, stream>>>(h->cfg, io);
     g_launches.fetch_add(1);
@@ -565,8 +567,10 @@ int cpmpc_create_ex(const cpmpc_params* params, int64_t batch, int device, uint3
   // device maximum.
   CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(prop.sharedMemPerBlockOptin)));
-  CUDA_TRY(cudaFuncSetAttribute(SelectKernel(lanes, true), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(prop.sharedMemPerBlockOptin)));
+  for (int mode = 1; mode <= 2; ++mode) {
+    CUDA_TRY(cudaFuncSetAttribute(SelectKernel(lanes, mode), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(prop.sharedMemPerBlockOptin)));
+  }
   int blocks_per_sm = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, 32 * wpb, h->smem_bytes));
   if (blocks_per_sm < 1) {
@@ -588,9 +592,9 @@ int cpmpc_create_ex(const cpmpc_params* params, int64_t batch, int device, uint3
   // Batches beyond one wave of the persistent grid run the serial rollouts of a Step in their own one-thread-per-
   // instance kernels (Launch): within one wave the step is the latency of ONE solve and two extra launches only add to
   // it.  The closed loop gains less (its fused form has no tail per control tick: warps run on into the next tick) and
-  // breaks even at about two waves (profiles/r02_x_ab_split_thresholds.jsonl).  Results do not depend on the choice.
+  // breaks even at about three waves (profiles/r02_y_closed_loop_split_vs_fused.jsonl).  Results do not depend on the choice.
   h->split = batch > n_groups;
-  h->split_loop = batch >= 2 * n_groups;
+  h->split_loop = batch >= 3 * n_groups;
   if ((flags & CPMPC_FLAG_SPLIT_LAUNCH) != 0u) h->split = h->split_loop = true;
   if ((flags & CPMPC_FLAG_FUSED_LAUNCH) != 0u) h->split = h->split_loop = false;
   if (const char* env = std::getenv("CPMPC_SPLIT")) h->split = h->split_loop = std::atoi(env) != 0;

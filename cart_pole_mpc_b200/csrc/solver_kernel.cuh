@@ -1554,10 +1554,11 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
 // ---------------------------------------------------------------------------------------------------------------------
 // Kernel: persistent grid-stride over instances; each warp carries 32/L instances at a time.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int L, bool LEAN = false>
+// SIM: the plant step of the fused closed loop is in this kernel (io.sim && !io.split decides at run time); the lean
+// instantiation without it serves every plain Step and the split closed loop.
+template <int L, bool LEAN = false, bool SIM = true>
 __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg, const KernelIO io) {
-  // LEAN (see solve_group): additionally no plant step inside this kernel (no closed loop, or a split launch)
-  const bool sim_here = LEAN ? false : (io.sim != 0 && !io.split);
+  const bool sim_here = SIM ? (io.sim != 0 && !io.split) : false;
   const int cps_guess = LEAN ? 1 : cfg.cps;
   const int WARPS_PER_BLOCK = blockDim.x >> 5;  // up to 8: two warps per SM sub-partition
   extern __shared__ double smem[];

@@ -114,8 +114,8 @@ int cpmpc_create(const cpmpc_params* params, int64_t batch, int device, cpmpc_ha
  *                           their own kernels with one thread per instance before and after the solve kernel, three
  *                           stream-ordered launches per control tick: 9 % more solves/s at 65536 instances, 12 % at
  *                           W = 160, nothing to gain while the batch is a single wave.  Without either flag the
- *                           library picks by batch size (split beyond one wave of the persistent grid, from two in
- *                           the closed loop).  Ignored (fused) under LOW_LATENCY / MIN_LATENCY. */
+ *                           library picks by batch size (split beyond one wave of the persistent grid, from three
+ *                           in the closed loop).  Ignored (fused) under LOW_LATENCY / MIN_LATENCY. */
 #define CPMPC_FLAG_SPLIT_LAUNCH 4u
 #define CPMPC_FLAG_FUSED_LAUNCH 8u
 int cpmpc_create_ex(const cpmpc_params* params, int64_t batch, int device, uint32_t flags, cpmpc_handle* out);
