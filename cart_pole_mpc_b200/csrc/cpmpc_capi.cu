@@ -111,7 +111,8 @@ using KernelFn = void (*)(const KernelCfg, const KernelIO);
 
 // mode 0: the general kernel.  1: the lean instantiation - no chunked linearisation, iteration log, debug view or
 // in-kernel plant step (solver_kernel.cuh LEAN) - for every plain Step and the split closed loop.  2: lean with the
-// plant step, for the fused closed loop.  Launch() picks per launch.
+// plant step, for the fused closed loop.  fixed: additionally the default problem shape (W = 40, S = 10, four lanes)
+// at compile time.  Launch() picks per launch.
 template <bool LEAN, bool SIM>
 KernelFn SelectKernelOf(int lanes) {
   switch (lanes) {
@@ -123,10 +124,13 @@ KernelFn SelectKernelOf(int lanes) {
     default: return cpmpc_solve_kernel<32, LEAN, SIM>;
   }
 }
-KernelFn SelectKernel(int lanes, int mode = 0) {
+KernelFn SelectKernel(int lanes, int mode = 0, bool fixed = false) {
+  if (fixed && lanes == 4 && mode == 1) return cpmpc_solve_kernel<4, true, false, true>;
+  if (fixed && lanes == 4 && mode == 2) return cpmpc_solve_kernel<4, true, true, true>;
   return mode == 2 ? SelectKernelOf<true, true>(lanes)
                    : mode == 1 ? SelectKernelOf<true, false>(lanes) : SelectKernelOf<false, true>(lanes);
 }
+bool DefaultShape(const KernelCfg& k) { return k.W == FX_W && k.S == FX_S && k.nseg == FX_NSEG && k.NS == FX_NS; }
 
 // Shared-memory layout of one instance (doubles).  `k.cps` must be set.
 void BuildLayout(KernelCfg& k) {
@@ -177,7 +181,7 @@ int Launch(cpmpc_solver* h, KernelIO io, cudaStream_t stream) {
   io.warp_cycles = h->d_warp_cycles;
   const bool split = (io.sim ? h->split_loop : h->split) && io.dbg == nullptr;
   const bool lean = h->cfg.cps == 1 && io.iter_log == nullptr && io.dbg == nullptr;
-  KernelFn fn = SelectKernel(h->lanes, lean ? ((io.sim != 0 && !split) ? 2 : 1) : 0);
+  KernelFn fn = SelectKernel(h->lanes, lean ? ((io.sim != 0 && !split) ? 2 : 1) : 0, DefaultShape(h->cfg));
   if (!split) {
     fn<<<h->grid, 32 * h->warps_per_block, h->smem_bytes, stream>>>(h->cfg, io);
     g_launches.fetch_add(1);
@@ -568,7 +572,8 @@ int cpmpc_create_ex(const cpmpc_params* params, int64_t batch, int device, uint3
   CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(prop.sharedMemPerBlockOptin)));
   for (int mode = 1; mode <= 2; ++mode) {
-    CUDA_TRY(cudaFuncSetAttribute(SelectKernel(lanes, mode), cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(SelectKernel(lanes, mode, DefaultShape(k)),
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(prop.sharedMemPerBlockOptin)));
   }
   int blocks_per_sm = 0;

@@ -39,6 +39,10 @@ namespace cpmpc {
 //   0 instance set-up + initial guess rollout   1 linearisation   2 condensed QP   3 Riccati recursion
 //   4 directional derivatives + penalty         5 line search (merit rollouts)   6 update / exit tests
 //   7 outputs (warm start, predicted-state rollout, statistics, plant step)
+// The default problem shape (OptimizationParams{}: window_length 40, state_spacing 10), for the instantiations that have
+// it at compile time (template parameter FX): loop bounds and the row strides of the Gamma / Z blocks become
+// immediates instead of registers and integer multiply-adds.
+constexpr int FX_W = 40, FX_S = 10, FX_NSEG = 4, FX_NS = 5, FX_N = 4 * FX_NS + FX_W;
 constexpr int N_PHASES = 8;
 constexpr int WARP_REC = 2 + N_PHASES;  // cycles, first instance of the last batch, then the phases
 
@@ -145,22 +149,23 @@ struct Ctx {
 // Cost terms over the controls (optimization.cc:270-301): 0.5 * sum of squared residuals for the columns owned by
 // this lane's segments.  `uu` is the control array in shared memory.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int L>
+template <int L, bool FX = false>
 __device__ __forceinline__ double control_cost_partial(const Ctx& c, const Weights& w, const double* uu,
                                                        const double u_prev) {
   const KernelCfg& k = *c.cfg;
+  const int W = FX ? FX_W : k.W, S = FX ? FX_S : k.S, nseg = FX ? FX_NSEG : k.nseg;
   // Branch-free: an absent cost family has weight 0 (its residuals add +0), the rate residual behind the last knot is
   // formed against the knot itself (0), and the one against the previous step's control is added on the lane that owns
   // knot 0.  The squares of the two families go to separate accumulators (two short dependent chains instead of one
   // chain through every term and a branch per term).
   double f_r = 0.0, f_u = 0.0;
-  for (int s = c.gl; s < k.nseg; s += L) {
-    const int c0 = s * k.S;
+  for (int s = c.gl; s < nseg; s += L) {
+    const int c0 = s * S;
     #pragma unroll 2
-    for (int i = 0; i < k.S; ++i) {
+    for (int i = 0; i < S; ++i) {
       const int col = c0 + i;
       const double uk = uu[col];
-      const double un = uu[(col + 1 < k.W) ? col + 1 : col];
+      const double un = uu[(col + 1 < W) ? col + 1 : col];
       const double rr = (uk - un) * w.w_r;
       const double ru = uk * w.w_u;
       f_r = fma(rr, rr, f_r);
@@ -176,6 +181,7 @@ __device__ __forceinline__ double control_cost_partial(const Ctx& c, const Weigh
 
 // Terminal cost / terminal equality / initial-state equality residuals (optimization.cc:228-267), evaluated by
 // one lane from the shooting states `xx` in shared memory.
+template <bool FX = false>
 __device__ __forceinline__ void boundary_terms(const KernelCfg& k, const Weights& w, const double* xx,
                                                const double x_cur[4], const double set_point, double& f_term,
                                                double& eq_bnd) {
@@ -190,7 +196,7 @@ __device__ __forceinline__ void boundary_terms(const KernelCfg& k, const Weights
     if (i == 1) d = mod_pi(d);
     eq_bnd += fabs(d);
   }
-  const double* xN = xx + 4 * (k.NS - 1);
+  const double* xN = xx + 4 * ((FX ? FX_NS : k.NS) - 1);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     double d = xN[i] - target[i];
@@ -250,7 +256,7 @@ __device__ __forceinline__ double rollout_defects(const double* __restrict__ dyn
   return eq;
 }
 
-template <int L, bool LEAN = false>
+template <int L, bool LEAN = false, bool FX = false>
 __device__ __forceinline__ void evaluate_errors(const Ctx& c, const Weights& w, const double* xx,
                                                 const double* uu, double* xk_out, const double x_cur[4],
                                                 const double set_point, const double u_prev, double& f_out,
@@ -258,11 +264,12 @@ __device__ __forceinline__ void evaluate_errors(const Ctx& c, const Weights& w, 
   const KernelCfg& k = *c.cfg;
   double eq = (!LEAN && k.cps > 1)
                   ? rollout_defects<L, true>(c.sm + k.off_dyn, xx, uu, xk_out, c.gl, k.nseg, k.S, k.cps, k.dt)
-                  : rollout_defects<L, false>(c.sm + k.off_dyn, xx, uu, xk_out, c.gl, k.nseg, k.S, 1, k.dt);
-  double f = control_cost_partial<L>(c, w, uu, u_prev);
+                  : rollout_defects<L, false>(c.sm + k.off_dyn, xx, uu, xk_out, c.gl, FX ? FX_NSEG : k.nseg,
+                                              FX ? FX_S : k.S, 1, k.dt);
+  double f = control_cost_partial<L, FX>(c, w, uu, u_prev);
   if (c.gl == 0) {
     double ft, eb;
-    boundary_terms(k, w, xx, x_cur, set_point, ft, eb);
+    boundary_terms<FX>(k, w, xx, x_cur, set_point, ft, eb);
     f += ft;
     eq += eb;
   }
@@ -297,11 +304,11 @@ __device__ __forceinline__ void evaluate_errors(const Ctx& c, const Weights& w, 
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int GAIN_STRIDE = XI_DIM + NR_MAX;  // doubles of feedback per knot: 5 for z, up to 5 for rho
 
-template <int L>
+template <int L, bool FX = false>
 __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights& w, const double lambda,
                                            const double x_cur[4], const double target[4], double& cdx) {
   const KernelCfg& k = *c.cfg;
-  const int W = k.W, S = k.S, NS = k.NS, nseg = k.nseg;
+  const int W = FX ? FX_W : k.W, S = FX ? FX_S : k.S, NS = FX ? FX_NS : k.NS, nseg = FX ? FX_NSEG : k.nseg;
   const double* xs = c.sm + k.off_xs;
   double* dxs = c.sm + k.off_dxs;
   double* du = c.sm + k.off_du;
@@ -636,11 +643,11 @@ __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights& w, const
 // of a second), useless on long unstable horizons (tests/prototypes/qp_riccati_proto.py) - the host picks.
 // Scratch (shared with the staging buffer of the Riccati recursion): Z [4][W], tinv [W].
 // ---------------------------------------------------------------------------------------------------------------------
-template <int L>
+template <int L, bool FX = false>
 __device__ __forceinline__ bool condensed_qp(const Ctx& c, const Weights& w, bool& tri_valid, const double x_cur[4],
                                              const double target[4], double& cdx) {
   const KernelCfg& k = *c.cfg;
-  const int W = k.W, S = k.S, NS = k.NS, nseg = k.nseg;
+  const int W = FX ? FX_W : k.W, S = FX ? FX_S : k.S, NS = FX ? FX_NS : k.NS, nseg = FX ? FX_NSEG : k.nseg;
   const double* xs = c.sm + k.off_xs;
   double* dxs = c.sm + k.off_dxs;
   double* du = c.sm + k.off_du;
@@ -1008,7 +1015,7 @@ struct SolveResult {
 // LEAN: the throughput mapping with nothing attached - one chunk per segment (cfg.cps == 1), no iteration log, no debug
 // view.  The host launches this instantiation whenever that holds (cpmpc_capi.cu SelectKernel); the paths it drops are
 // 40 % of the general kernel's instructions, never executed there but in the way of its register allocation.
-template <int L, bool LEAN = false>
+template <int L, bool LEAN = false, bool FX = false>
 __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, const Weights& w,
                                             const double x_cur[4], const double& set_point, const double& u_prev,
                                             double* iter_log, SolveResult& res, long long* ph, double* dbg = nullptr,
@@ -1035,7 +1042,8 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
   double* Gam = c.sm + k.off_gam;
   constexpr double half_pi = 1.5707963267948966;
   const double target[4] = {set_point, half_pi, 0.0, 0.0};
-  const int W = k.W, S = k.S, NS = k.NS, nseg = k.nseg, cps = LEAN ? 1 : k.cps;
+  const int W = FX ? FX_W : k.W, S = FX ? FX_S : k.S, NS = FX ? FX_NS : k.NS, nseg = FX ? FX_NSEG : k.nseg;
+  const int cps = LEAN ? 1 : k.cps, nchunk = LEAN ? nseg : k.nchunk;
 
   // Cold solver scalars: kept in a struct whose address escapes, so that CPMPC_PARK() moves them out of the
   // register file for the duration of the rollout loops (see CPMPC_PARK).
@@ -1113,7 +1121,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
       CPMPC_PARK();
       DynConst P;
       load_dyn_const(P, c.sm + k.off_dyn);
-      for (int id = c.gl; id < k.nchunk; id += L) {
+      for (int id = c.gl; id < nchunk; id += L) {
         const int s = id / cps, cc = id - s * cps;
         const int i0 = (cc * S) / cps, i1 = ((cc + 1) * S) / cps;
         const double* x0 = (cc == 0) ? (xs + 4 * s) : (xk + 4 * id);
@@ -1178,10 +1186,10 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
         // stitch the chunks of a segment: Phi_s = Phi_{cps-1} ... Phi_0, Gamma_j <- (Phi_{cps-1} ... Phi_{cc+1}) Gamma_j
         CPMPC_GSYNC();
         #pragma unroll 1
-        for (int base = 0; base < k.nchunk; base += L) {  // uniform trip count: the loop body synchronises
+        for (int base = 0; base < nchunk; base += L) {  // uniform trip count: the loop body synchronises
           const int id = base + c.gl;
           const int s = id / cps, cc = id - s * cps;
-          const bool mine = id < k.nchunk && cc < cps - 1;
+          const bool mine = id < nchunk && cc < cps - 1;
           double Sx[16], Pr[16];
           if (mine) {
             const double* last = PhiC + 16 * (s * cps + cps - 1);
@@ -1239,7 +1247,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
       double f_part = control_cost_partial<L>(c, w, u, u_prev);
       if (c.gl == 0) {
         double ft, eb;
-        boundary_terms(k, w, xs, x_cur, set_point, ft, eb);
+        boundary_terms<FX>(k, w, xs, x_cur, set_point, ft, eb);
         f_part += ft;
         eq_part += eb;
       }
@@ -1274,7 +1282,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
     if (active) {
       const bool try_condensed = (dbg != nullptr && dbg_qp != 0) ? (dbg_qp == 2) : (k.condensed && !(lambda > 0.0));
       if (try_condensed) {
-        qp_ok = condensed_qp<L>(c, w, tri_valid, x_cur, target, cdx);
+        qp_ok = condensed_qp<L, FX>(c, w, tri_valid, x_cur, target, cdx);
         // A failed 4x4 multiplier system is a property of the condensed formulation (open-loop sensitivity rows nearly
         // dependent), not necessarily of the QP: restore the gradient and let the Riccati recursion decide.
         if (!qp_ok) fill_gradient();
@@ -1283,7 +1291,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
       if (need_riccati) tri_valid = false;  // the Riccati stage matrix shares the scratch of the tridiagonal factor
     }
     CPMPC_MARK(2);
-    if (need_riccati) qp_ok = riccati_qp<L>(c, w, lambda, x_cur, target, cdx);
+    if (need_riccati) qp_ok = riccati_qp<L, FX>(c, w, lambda, x_cur, target, cdx);
     CPMPC_MARK(3);
     if (active) {
       if (dbg != nullptr) {
@@ -1454,7 +1462,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
         }
         CPMPC_GSYNC();
         CPMPC_PARK();
-        evaluate_errors<L, LEAN>(c, w, xc, uc, xkc, x_cur, set_point, u_prev, step_f, step_eq);
+        evaluate_errors<L, LEAN, FX>(c, w, xc, uc, xkc, x_cur, set_point, u_prev, step_f, step_eq);
         CPMPC_PARK();
         CPMPC_GSYNC();
         if (lrow != nullptr && c.gl == 0 && n_steps < 6) {
@@ -1496,7 +1504,7 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
         for (int col = c.gl; col < W; col += L) u[col] = uc[col];
         if (cps > 1)
           #pragma unroll 1
-          for (int q = c.gl; q < 4 * k.nchunk; q += L) xk[q] = xkc[q];
+          for (int q = c.gl; q < 4 * nchunk; q += L) xk[q] = xkc[q];
         CPMPC_GSYNC();
         lambda = fmax(lambda * ((opt_state == OS_RESTORE_LM) ? k.lam_dec_restore : k.lam_dec_success), k.lam_min);
         opt_state = OS_NOMINAL;
@@ -1556,7 +1564,8 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
 // ---------------------------------------------------------------------------------------------------------------------
 // SIM: the plant step of the fused closed loop is in this kernel (io.sim && !io.split decides at run time); the lean
 // instantiation without it serves every plain Step and the split closed loop.
-template <int L, bool LEAN = false, bool SIM = true>
+// FX: the problem has the default shape (FX_W, FX_S), known at compile time.
+template <int L, bool LEAN = false, bool SIM = true, bool FX = false>
 __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg, const KernelIO io) {
   const bool sim_here = SIM ? (io.sim != 0 && !io.split) : false;
   const int cps_guess = LEAN ? 1 : cfg.cps;
@@ -1574,7 +1583,7 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
   const long long n_groups = (long long)gridDim.x * WARPS_PER_BLOCK * G;
   c.sm = smem + (size_t)(warp * G + g) * cfg.stride;
   c.kk = io.kk_scratch + (size_t)group_id * cfg.kk_stride;
-  const int W = cfg.W, S = cfg.S, NS = cfg.NS, N = cfg.N;
+  const int W = FX ? FX_W : cfg.W, S = FX ? FX_S : cfg.S, NS = FX ? FX_NS : cfg.NS, N = FX ? FX_N : cfg.N;
   double* xs = c.sm + cfg.off_xs;
   double* u = c.sm + cfg.off_u;
 
@@ -1710,7 +1719,7 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
         ph[0] += now - ph[N_PHASES];
         ph[N_PHASES] = now;
       }
-      solve_group<L, LEAN>(c, have, w, x_cur, set_point, u_prev, ilog, res, ph, dbg, io.dbg_lambda, io.dbg_qp);
+      solve_group<L, LEAN, FX>(c, have, w, x_cur, set_point, u_prev, ilog, res, ph, dbg, io.dbg_lambda, io.dbg_qp);
 
       if (have) {
         // ---- outputs (optimization.cc:83-96) ------------------------------------------------------------------
