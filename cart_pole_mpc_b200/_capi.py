@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = (
     "cpmpc_set_previous_solution",
     "cpmpc_get_previous_solution", "cpmpc_enable_iteration_log", "cpmpc_get_iteration_log", "cpmpc_sim_step_device",
     "cpmpc_sim_step", "cpmpc_closed_loop", "cpmpc_closed_loop_device", "cpmpc_launch_count",
-    "cpmpc_measure_fp64_peak", "cpmpc_debug_fastmath", "cpmpc_debug_stride", "cpmpc_debug_first_qp", "cpmpc_get_warp_cycles",
+    "cpmpc_measure_fp64_peak", "cpmpc_debug_fastmath", "cpmpc_debug_stride", "cpmpc_debug_first_qp", "cpmpc_get_warp_cycles", "cpmpc_enable_phase_clocks",
     "cpmpc_plant_state_dim", "cpmpc_plant_dyn_dim", "cpmpc_plant_default_params", "cpmpc_plant_create",
     "cpmpc_plant_destroy", "cpmpc_plant_solution_dim", "cpmpc_plant_step", "cpmpc_plant_step_device",
     "cpmpc_plant_reset", "cpmpc_plant_reset_device", "cpmpc_plant_set_previous_solution",
@@ -162,6 +162,8 @@ def lib() -> C.CDLL:
     L.cpmpc_measure_fp64_peak.argtypes = [C.c_int, dp]
     L.cpmpc_debug_fastmath.restype = C.c_int
     L.cpmpc_debug_fastmath.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+    L.cpmpc_enable_phase_clocks.restype = C.c_int
+    L.cpmpc_enable_phase_clocks.argtypes = [vp, C.c_int]
     L.cpmpc_get_warp_cycles.restype = C.c_int64
     L.cpmpc_get_warp_cycles.argtypes = [vp, vp, C.c_int64]
     L.cpmpc_debug_stride.restype = C.c_int64

@@ -204,6 +204,11 @@ class BatchedOptimization:
     PHASE_NAMES = ("setup+initial guess", "linearise", "condensed qp", "riccati qp", "derivatives+penalty",
                    "line search", "update+exit tests", "outputs")
 
+    def enable_phase_clocks(self, enable: bool = True) -> None:
+        """cpmpc_enable_phase_clocks: launches made afterwards fill the per-phase entries of `warp_cycles` (1.5 % slower;
+        same results)."""
+        _capi.check(self._lib.cpmpc_enable_phase_clocks(self._h, 1 if enable else 0))
+
     def warp_cycles(self, with_instances: bool = False) -> np.ndarray:
         """SM cycles every warp of the last launch spent on its instances (cpmpc_get_warp_cycles); with
         `with_instances` the full [n, 10] records: cycles, first instance of the warp's last batch, then the cycles per

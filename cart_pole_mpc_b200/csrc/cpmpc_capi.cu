@@ -67,6 +67,7 @@ struct cpmpc_solver {
   // split launch (large batches): shooting states of the initial guess [B, 4 NS] from cpmpc_guess_kernel, and the
   // controls for cpmpc_post_kernel when the caller asked for no u_out
   bool split = false, split_loop = false;  // Step / closed loop
+  bool phase_clocks = false;  // cpmpc_enable_phase_clocks: launch the general kernel, which times its phases
   double* d_guess = nullptr;
   double* d_u_split = nullptr;
   unsigned long long* d_queue = nullptr;
@@ -180,7 +181,7 @@ int Launch(cpmpc_solver* h, KernelIO io, cudaStream_t stream) {
   io.iter_log = h->log_enabled ? h->d_iter_log : nullptr;
   io.warp_cycles = h->d_warp_cycles;
   const bool split = (io.sim ? h->split_loop : h->split) && io.dbg == nullptr;
-  const bool lean = h->cfg.cps == 1 && io.iter_log == nullptr && io.dbg == nullptr;
+  const bool lean = h->cfg.cps == 1 && io.iter_log == nullptr && io.dbg == nullptr && !h->phase_clocks;
   KernelFn fn = SelectKernel(h->lanes, lean ? ((io.sim != 0 && !split) ? 2 : 1) : 0, DefaultShape(h->cfg));
   if (!split) {
     fn<<<h->grid, 32 * h->warps_per_block, h->smem_bytes, stream>>>(h->cfg, io);
@@ -987,6 +988,12 @@ int cpmpc_closed_loop(cpmpc_handle h, int64_t n_steps, double* states, const dou
     CUDA_TRY(cudaMemcpyAsync(stats_sum_out, h->d_stats_sum, sizeof(long long) * 4, cudaMemcpyDeviceToHost, s));
   }
   CUDA_TRY(cudaStreamSynchronize(s));
+  return CPMPC_OK;
+}
+
+int cpmpc_enable_phase_clocks(cpmpc_handle h, int enable) {
+  if (h == nullptr) return Fail(CPMPC_ERR_INVALID_ARGUMENT, "null handle");
+  h->phase_clocks = enable != 0;
   return CPMPC_OK;
 }
 

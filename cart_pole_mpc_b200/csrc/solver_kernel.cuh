@@ -1021,11 +1021,15 @@ __device__ __forceinline__ void solve_group(const Ctx& c, const bool active_in, 
                                             double* iter_log, SolveResult& res, long long* ph, double* dbg = nullptr,
                                             const double dbg_lambda = 0.0, const int dbg_qp = 0) {
   // ph[0..N_PHASES) accumulate cycles per phase, ph[N_PHASES] is the time of the last mark
-#define CPMPC_MARK(idx)                 \
-  do {                                  \
-    const long long now_ = clock64();   \
-    ph[idx] += now_ - ph[N_PHASES];     \
-    ph[N_PHASES] = now_;                \
+  // (not in the lean instantiations: eight clock reads and local-memory updates per iteration are 1.5 % of a step;
+  // cpmpc_enable_phase_clocks selects the general kernel, which keeps them)
+#define CPMPC_MARK(idx)                   \
+  do {                                    \
+    if (!LEAN) {                          \
+      const long long now_ = clock64();   \
+      ph[idx] += now_ - ph[N_PHASES];     \
+      ph[N_PHASES] = now_;                \
+    }                                     \
   } while (0)
   const KernelCfg& k = *c.cfg;
   double* xs = c.sm + k.off_xs;
@@ -1714,7 +1718,7 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
                          ? io.iter_log + (size_t)inst * cfg.max_iter * CPMPC_ITERLOG_STRIDE
                          : nullptr;
       double* dbg = (!LEAN && io.dbg != nullptr && have) ? io.dbg + (size_t)inst * io.dbg_stride : nullptr;
-      {
+      if (!LEAN) {
         const long long now = clock64();
         ph[0] += now - ph[N_PHASES];
         ph[N_PHASES] = now;
@@ -1801,7 +1805,7 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
         }
         CPMPC_GSYNC();
       }
-      {
+      if (!LEAN) {
         const long long now = clock64();
         ph[7] += now - ph[N_PHASES];
         ph[N_PHASES] = now;

@@ -220,6 +220,10 @@ int cpmpc_debug_first_qp(cpmpc_handle h, const double* states, const double* dyn
  * nothing when cycles_out is NULL or capacity is too small; -1 on error. */
 #define CPMPC_WARP_RECORD 10
 int64_t cpmpc_get_warp_cycles(cpmpc_handle h, uint64_t* cycles_out, int64_t capacity);
+/* The per-phase entries of that record are only filled by launches made after cpmpc_enable_phase_clocks(h, 1): eight
+ * clock reads per SQP iteration cost 1.5 % of a step, so the kernels the library launches by default record the total
+ * and the instance only (phases 0).  Enabling selects the general kernel instantiation (same results, bit for bit). */
+int cpmpc_enable_phase_clocks(cpmpc_handle h, int enable);
 
 /* Number of kernel launches issued by this library since load (for bench accounting). */
 int64_t cpmpc_launch_count(void);

@@ -38,6 +38,7 @@ def run(name):
     std, dyd, spd = to(st), to(dy), to(sp)
     wd = to(weights) if weights is not None else None
     s = BatchedOptimization(B, **over)
+    s.enable_phase_clocks()  # the general kernel instantiation: 1.5 % slower than the lean one the library launches by default
     u = torch.empty((B, s.W), dtype=torch.float64, device=dev)
     pred = torch.empty((B, s.W, 4), dtype=torch.float64, device=dev)
     ts = []

@@ -40,6 +40,13 @@ def main():
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         s = np.frombuffer(stats.cpu().numpy().tobytes(), dtype=np.dtype(_capi.STATS_DTYPE))
+        if "--why" in sys.argv:
+            # one more (untimed) launch through the general kernel, which times its phases (1.5 % slower)
+            solver.enable_phase_clocks(True)
+            solver.reset_device()
+            solver.step_device(std, dyd, spd, u, pred_out=pred, stats_out=stats)
+            torch.cuda.synchronize()
+            solver.enable_phase_clocks(False)
         wci = solver.warp_cycles(with_instances=True)
         wci = wci[wci[:, 0] > 0]
         wc = wci[:, 0].astype(np.float64)

@@ -967,3 +967,25 @@ def test_far_out_pole_angles_are_wrapped_on_the_way_in(oracle):
     ref = oracle.batch_step(oracle.opt_array(), far, dy, sp, want_iter_log=False)
     rel = _rel_cost(a, ref.stats)
     assert np.median(rel) < 1e-6 and (rel <= 1e-4).mean() >= 0.9, rel
+
+
+def test_phase_clocks_are_opt_in_and_change_nothing():
+    """cpmpc_enable_phase_clocks: the default (lean) kernels record only a warp's total cycles and its last batch; with
+    the clocks enabled the general kernel fills the per-phase entries, which then add up to the total, and the results
+    are the same bits."""
+    from cart_pole_mpc_b200 import synthetic
+    B = 512
+    st, dy, sp = synthetic.swingup_batch(B, seed=3)
+    s = _solver(B)
+    a = s.step(st, dy, sp)
+    rec = s.warp_cycles(with_instances=True).astype(np.int64)
+    rec = rec[rec[:, 0] > 0]
+    assert rec.shape[0] == B // 8 and np.all(rec[:, 2:] == 0)
+    s.reset()
+    s.enable_phase_clocks(True)
+    b = s.step(st, dy, sp)
+    rec = s.warp_cycles(with_instances=True).astype(np.int64)
+    rec = rec[rec[:, 0] > 0]
+    assert np.all(rec[:, 2:].sum(axis=1) > 0.95 * rec[:, 0]) and np.all(rec[:, 2:].sum(axis=1) <= rec[:, 0])
+    assert np.array_equal(a.u, b.u) and np.array_equal(a.predicted_states, b.predicted_states)
+    assert a.stats.tobytes() == b.stats.tobytes()
