@@ -969,23 +969,26 @@ def test_far_out_pole_angles_are_wrapped_on_the_way_in(oracle):
     assert np.median(rel) < 1e-6 and (rel <= 1e-4).mean() >= 0.9, rel
 
 
-def test_phase_clocks_are_opt_in_and_change_nothing():
+@pytest.mark.parametrize("over", [dict(), dict(u_cost_weight=0.0), dict(window_length=160)],
+                         ids=["defaults", "lm_heavy", "w160"])
+def test_phase_clocks_are_opt_in_and_change_nothing(over):
     """cpmpc_enable_phase_clocks: the default (lean) kernels record only a warp's total cycles and its last batch; with
     the clocks enabled the general kernel fills the per-phase entries, which then add up to the total, and the results
-    are the same bits."""
+    are the same bits - also where the Riccati recursion does the work (damped iterations, W = 160), whose sums the
+    compiler contracts as it sees fit in each instantiation."""
     from cart_pole_mpc_b200 import synthetic
     B = 512
-    st, dy, sp = synthetic.swingup_batch(B, seed=3)
-    s = _solver(B)
+    st, dy, sp = synthetic.swingup_batch(B, seed=13)
+    s = _solver(B, **over)
     a = s.step(st, dy, sp)
     rec = s.warp_cycles(with_instances=True).astype(np.int64)
     rec = rec[rec[:, 0] > 0]
-    assert rec.shape[0] == B // 8 and np.all(rec[:, 2:] == 0)
+    assert rec.shape[0] == B // (8 if s.W == 40 else 4) and np.all(rec[:, 2:] == 0)
     s.reset()
     s.enable_phase_clocks(True)
     b = s.step(st, dy, sp)
     rec = s.warp_cycles(with_instances=True).astype(np.int64)
     rec = rec[rec[:, 0] > 0]
     assert np.all(rec[:, 2:].sum(axis=1) > 0.95 * rec[:, 0]) and np.all(rec[:, 2:].sum(axis=1) <= rec[:, 0])
-    assert np.array_equal(a.u, b.u) and np.array_equal(a.predicted_states, b.predicted_states)
+    assert np.array_equal(a.u, b.u, equal_nan=True) and np.array_equal(a.predicted_states, b.predicted_states, equal_nan=True)
     assert a.stats.tobytes() == b.stats.tobytes()
