@@ -113,7 +113,7 @@ using KernelFn = void (*)(const KernelCfg, const KernelIO);
 // mode 0: the general kernel.  1: the lean instantiation - no chunked linearisation, iteration log, debug view or
 // in-kernel plant step (solver_kernel.cuh LEAN) - for every plain Step and the split closed loop.  2: lean with the
 // plant step, for the fused closed loop.  fixed: additionally the default problem shape (W = 40, S = 10, four lanes)
-// at compile time.  Launch() picks per launch.
+// at compile time and the handle's weights for every instance (no per-instance weights in the call).  Launch() picks per launch.
 template <bool LEAN, bool SIM>
 KernelFn SelectKernelOf(int lanes) {
   switch (lanes) {
@@ -182,7 +182,7 @@ int Launch(cpmpc_solver* h, KernelIO io, cudaStream_t stream) {
   io.warp_cycles = h->d_warp_cycles;
   const bool split = (io.sim ? h->split_loop : h->split) && io.dbg == nullptr;
   const bool lean = h->cfg.cps == 1 && io.iter_log == nullptr && io.dbg == nullptr && !h->phase_clocks;
-  KernelFn fn = SelectKernel(h->lanes, lean ? ((io.sim != 0 && !split) ? 2 : 1) : 0, DefaultShape(h->cfg));
+  KernelFn fn = SelectKernel(h->lanes, lean ? ((io.sim != 0 && !split) ? 2 : 1) : 0, DefaultShape(h->cfg) && io.weights == nullptr);
   if (!split) {
     fn<<<h->grid, 32 * h->warps_per_block, h->smem_bytes, stream>>>(h->cfg, io);
     g_launches.fetch_add(1);
@@ -573,9 +573,11 @@ int cpmpc_create_ex(const cpmpc_params* params, int64_t batch, int device, uint3
   CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(prop.sharedMemPerBlockOptin)));
   for (int mode = 1; mode <= 2; ++mode) {
-    CUDA_TRY(cudaFuncSetAttribute(SelectKernel(lanes, mode, DefaultShape(k)),
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(prop.sharedMemPerBlockOptin)));
+    for (int fixed = 0; fixed <= 1; ++fixed) {  // per-instance weights select the non-fixed instantiation at launch
+      CUDA_TRY(cudaFuncSetAttribute(SelectKernel(lanes, mode, fixed != 0 && DefaultShape(k)),
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(prop.sharedMemPerBlockOptin)));
+    }
   }
   int blocks_per_sm = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, 32 * wpb, h->smem_bytes));

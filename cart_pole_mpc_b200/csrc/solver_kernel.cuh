@@ -316,7 +316,10 @@ __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights& w, const
   const double* ev = c.sm + k.off_e;
   const double* Gam = c.sm + k.off_gam;
   double* stage = c.sm + k.off_aug;  // [S][GAIN_STRIDE] feedback rows of one segment, staged for the forward sweep
-  const double wu2 = w.w_u * w.w_u, wr2 = w.w_r * w.w_r;
+  // Squares of the weights as explicit, separately rounded products: written `w * w`, whether the compiler contracts one
+  // of them into the sum it feeds (the pivot's `wu2 + lambda + wr2`, the terminal `lambda + w2`) depends on what else
+  // it sees of the weights in the instantiation at hand, and the instantiations of this kernel must agree bit for bit.
+  const double wu2 = __dmul_rn(w.w_u, w.w_u), wr2 = __dmul_rn(w.w_r, w.w_r);
   cdx = 0.0;
 
   // hard terminal rows (negative weight, optimization.cc:236-267) and their rho coordinates
@@ -371,7 +374,7 @@ __device__ __forceinline__ bool riccati_qp(const Ctx& c, const Weights& w, const
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const bool soft = w.wt[i] >= 0.0;
-      const double w2 = soft ? w.wt[i] * w.wt[i] : 0.0;
+      const double w2 = soft ? __dmul_rn(w.wt[i], w.wt[i]) : 0.0;
       P[i][i] = lambda + w2;
       Q[i][0] = w2 * dT[i];
 #pragma unroll
@@ -1623,14 +1626,26 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
     } kc;
     long long* ph = wph.ph;
     asm volatile("" : : "l"(&kc) : "memory");
-    Weights& w = kc.w;
+    // FX instantiations are launched without per-instance weights only (cpmpc_capi.cu Launch): the weights are the
+    // handle's, i.e. kernel parameters, and a local that never escapes lets the compiler read them from the constant
+    // bank where they are used instead of keeping a per-thread copy in (parked) local memory
+    Weights w_uniform;
+    if (FX) {
+      w_uniform.w_u = (cfg.w_u > 0.0) ? cfg.w_u : 0.0;
+      w_uniform.w_r = (cfg.w_r > 0.0) ? cfg.w_r : 0.0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w_uniform.wt[i] = cfg.wt[i];
+    }
+    Weights& w = FX ? w_uniform : kc.w;
     double(&x_cur)[4] = kc.x_cur;
     double& set_point = kc.set_point;
     x_cur[0] = x_cur[1] = x_cur[2] = x_cur[3] = 0.0;
     set_point = 0.0;
     if (have) {
       if (c.gl == 0) store_dyn_const(c.sm + cfg.off_dyn, make_dyn_const(io.dyn + inst * CPMPC_DYN_STRIDE));
-      if (io.weights != nullptr) {
+      if (FX) {
+        // (uniform weights, above)
+      } else if (io.weights != nullptr) {
         const double* pw = io.weights + inst * CPMPC_WEIGHTS_STRIDE;
         w.w_u = pw[0];
         w.w_r = pw[1];
@@ -1642,8 +1657,10 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
 #pragma unroll
         for (int i = 0; i < 4; ++i) w.wt[i] = cfg.wt[i];
       }
-      if (!(w.w_u > 0.0)) w.w_u = 0.0;
-      if (!(w.w_r > 0.0)) w.w_r = 0.0;
+      if (!FX) {
+        if (!(w.w_u > 0.0)) w.w_u = 0.0;
+        if (!(w.w_r > 0.0)) w.w_r = 0.0;
+      }
       const double* ps = (io.sim ? io.states_io : io.states) + inst * CPMPC_STATE_STRIDE;
 #pragma unroll
       for (int i = 0; i < 4; ++i) x_cur[i] = ps[i];
@@ -1651,8 +1668,10 @@ __global__ void __launch_bounds__(256, 1) cpmpc_solve_kernel(const KernelCfg cfg
       set_point = io.set_points[inst];
     } else {
       if (c.gl == 0) store_dyn_const(c.sm + cfg.off_dyn, dummy_dyn_const());
-      w.w_u = w.w_r = 1.0;
-      w.wt[0] = w.wt[1] = w.wt[2] = w.wt[3] = 1.0;
+      if (!FX) {
+        w.w_u = w.w_r = 1.0;
+        w.wt[0] = w.wt[1] = w.wt[2] = w.wt[3] = 1.0;
+      }
     }
 
     CPMPC_GSYNC();
