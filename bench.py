@@ -333,7 +333,7 @@ def _sum_over_ranks(dist, dev, values):
 
 def run_closed_loop(args, embedded=False):
     """configs[2]: receding-horizon MPC, B plants x n control steps, warm-started solves, plant integrated on the
-    device between solves (no host round trip inside the loop: one fused launch, or from two waves of instances three
+    device between solves (no host round trip inside the loop: one fused launch, or from three waves of instances three
     stream-ordered kernels per control tick).  A "step" of the bench = the whole closed loop."""
     import torch
     from cart_pole_mpc_b200 import BatchedOptimization, measure_fp64_peak, launch_count, synthetic
